@@ -1,0 +1,184 @@
+#!/usr/bin/env python3
+"""Generate ``tests/golden/*`` from the UNMODIFIED reference, imported from /root/reference.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+The reference's loader modules import packages that are absent here (librosa, soundfile, pydub,
+torchaudio.io, torchaudio.sox_effects); five empty stub modules are registered first so that
+``datautils.asvspoof_2019_augall_3`` imports unmodified. Nothing is copied from the
+reference: the fixtures hold *outputs* of its functions on seeded synthetic inputs, plus the state
+of the global numpy stream after each call (to pin how many draws each operator consumes).
+
+Inputs are not stored: they are regenerated from ``synth_utterance(u, L, loud)`` and
+``np.random.seed(seed_for(u))`` (oracle/rawboost_oracle.py), exactly as the tests do.
+"""
+import hashlib
+import json
+import os
+import sys
+import tempfile
+import types
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+sys.path.insert(0, ROOT)
+from oracle.rawboost_oracle import make_args, seed_for, synth_utterance  # noqa: E402
+
+
+def import_reference():
+    """Import the reference operators and one loader's dispatcher, unmodified."""
+    import importlib
+    for name in ("librosa", "soundfile", "pydub", "torchaudio", "torchaudio.functional",
+                 "torchaudio.io", "torchaudio.sox_effects"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = types.ModuleType(name)
+    for mod, attr, val in (("pydub", "AudioSegment", type("AudioSegment", (), {})),
+                           ("torchaudio.io", "AudioEffector", type("AudioEffector", (), {})),
+                           ("torchaudio.sox_effects", "apply_effects_tensor", lambda *a, **k: None)):
+        if not hasattr(sys.modules[mod], attr):
+            setattr(sys.modules[mod], attr, val)
+    for sub in ("functional", "io", "sox_effects"):
+        if not hasattr(sys.modules["torchaudio"], sub):
+            setattr(sys.modules["torchaudio"], sub, sys.modules["torchaudio." + sub])
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp())  # the loader's logging.basicConfig drops errors.log into CWD
+    try:
+        import datautils.RawBoost as rb
+        import datautils.asvspoof_2019_augall_3 as loader
+    finally:
+        os.chdir(cwd)
+    assert loader.LnL_convolutive_noise is rb.LnL_convolutive_noise
+    return rb, loader
+
+
+def stream_digest():
+    """Compact fingerprint of the global legacy stream (position + key hash + gauss cache)."""
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    return {
+        "pos": int(pos),
+        "key_sha1": hashlib.sha1(np.asarray(key, dtype=np.uint32).tobytes()).hexdigest(),
+        "has_gauss": int(has_gauss),
+        "cached_gaussian": float(cached),
+    }
+
+
+def summarise(y):
+    y64 = np.asarray(y, dtype=np.float64)
+    probe = np.linspace(0, y64.shape[0] - 1, 64).astype(np.int64)
+    return {
+        "dtype": str(np.asarray(y).dtype),
+        "sum": float(y64.sum()),
+        "sumsq": float((y64 * y64).sum()),
+        "min": float(y64.min()),
+        "max": float(y64.max()),
+        "argmax_abs": int(np.argmax(np.abs(y64))),
+        "probe_idx": probe.tolist(),
+        "probe_val": y64[probe].tolist(),
+    }
+
+
+def main():
+    warnings.simplefilter("ignore", DeprecationWarning)  # int(ndarray) at RawBoost.py:17
+    rb, loader = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    args = make_args()
+    arrays = {}
+    meta = {"numpy": np.__version__, "cases": {}, "ops": {}, "full": {}}
+    import scipy
+    meta["scipy"] = scipy.__version__
+
+    # ---- dispatcher, every algo, two amplitude variants, short utterances (arrays kept) ----
+    L_small = 16000
+    for algo in range(0, 9):
+        for loud in (0, 1):
+            for u in (0, 1):
+                x = synth_utterance(u, L_small, bool(loud))
+                np.random.seed(seed_for(u))
+                y = loader.process_Rawboost_feature(x, 16000, args, algo)
+                key = f"algo{algo}_loud{loud}_u{u}"
+                arrays[key] = np.asarray(y)
+                meta["cases"][key] = {"algo": algo, "loud": loud, "u": u, "L": L_small,
+                                      "dtype": str(np.asarray(y).dtype), "stream": stream_digest(),
+                                      "same_object": bool(y is x)}
+
+    # ---- ragged / tiny lengths through the dispatcher (algo 5) ----
+    for L in (1, 2, 37, 600, 4097):
+        x = synth_utterance(7, L, False)
+        np.random.seed(seed_for(7))
+        y = loader.process_Rawboost_feature(x, 16000, args, 5)
+        key = f"ragged_algo5_L{L}"
+        arrays[key] = np.asarray(y)
+        meta["cases"][key] = {"algo": 5, "loud": 0, "u": 7, "L": L, "dtype": str(np.asarray(y).dtype),
+                              "stream": stream_digest(), "same_object": False}
+
+    # ---- operator surface ----
+    for u in range(6):
+        np.random.seed(seed_for(u))
+        b = rb.genNotchCoeffs(5, 20, 8000, 100, 1000, 10, 100, 0, 0, 16000)
+        arrays[f"notch_u{u}"] = b
+        meta["ops"][f"notch_u{u}"] = {"K": int(b.shape[0]), "stream": stream_digest()}
+    # low>high gain range, as LnL uses from order 2 on
+    np.random.seed(99)
+    b = rb.genNotchCoeffs(5, 20, 8000, 100, 1000, 10, 100, -5, -20, 16000)
+    arrays["notch_gain"] = b
+    meta["ops"]["notch_gain"] = {"K": int(b.shape[0]), "stream": stream_digest()}
+
+    rs = np.random.RandomState(5)
+    for K in (1, 2, 3, 4, 11, 64, 491):
+        xs = rs.standard_normal(300).astype(np.float32)
+        bs = rs.standard_normal(K)
+        arrays[f"fir_x_K{K}"] = xs
+        arrays[f"fir_b_K{K}"] = bs
+        arrays[f"fir_y_K{K}"] = rb.filterFIR(xs, bs)
+    for tag, v in (("quiet", 0.5), ("loud", 3.0)):
+        xs = (v * rs.uniform(-1, 1, 257)).astype(np.float32)
+        arrays[f"norm_x_{tag}"] = xs
+        arrays[f"norm_y0_{tag}"] = rb.normWav(xs, 0)
+        arrays[f"norm_y1_{tag}"] = rb.normWav(xs, 1)
+    np.random.seed(3)
+    meta["ops"]["randRange"] = {
+        "float": float(rb.randRange(20, 8000, 0)[0]),
+        "int": int(rb.randRange(10, 100, 1)),
+        "reversed": float(rb.randRange(-5, -20, 0)[0]),
+        "stream": stream_digest(),
+    }
+    for u in (0, 1):
+        x = synth_utterance(u, L_small, False)
+        np.random.seed(seed_for(u))
+        arrays[f"op_lnl_u{u}"] = rb.LnL_convolutive_noise(x, 5, 5, 20, 8000, 100, 1000, 10, 100, 0, 0, 5, 20, 16000)
+        np.random.seed(seed_for(u))
+        arrays[f"op_isd_u{u}"] = rb.ISD_additive_noise(x, 10, 2)
+        np.random.seed(seed_for(u))
+        arrays[f"op_ssi_u{u}"] = rb.SSI_additive_noise(x, 10, 40, 5, 20, 8000, 100, 1000, 10, 100, 0, 0, 16000)
+
+    # ---- BASELINE-size utterances (64600): summaries only ----
+    for algo in (1, 2, 3, 4, 5, 8):
+        for loud in (0, 1):
+            for u in (0, 3):
+                x = synth_utterance(u, 64600, bool(loud))
+                np.random.seed(seed_for(u))
+                y = loader.process_Rawboost_feature(x, 16000, args, algo)
+                s = summarise(y)
+                s["stream"] = stream_digest()
+                meta["full"][f"algo{algo}_loud{loud}_u{u}"] = s
+
+    np.savez_compressed(os.path.join(OUT, "rawboost_golden.npz"), **arrays)
+    with open(os.path.join(OUT, "rawboost_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    size = os.path.getsize(os.path.join(OUT, "rawboost_golden.npz"))
+    print(f"wrote {len(arrays)} arrays ({size/1e6:.2f} MB) and {len(meta['cases'])+len(meta['full'])} case records to {OUT}")
+
+
+if __name__ == "__main__":
+    main()
