@@ -1,0 +1,152 @@
+/*
+ * rawboost_b200.h -- C ABI of the B200-native RawBoost waveform-augmentation path.
+ *
+ * The reference (josebeo2016/SCL-Deepfake-audio-detection) has no FFI of its own: its callers bind to
+ * plain Python symbols in datautils/RawBoost.py. This header is the boundary a
+ * maintainer binds instead (ctypes stub in INTEGRATION.md); every entry point names the reference
+ * function it replaces. Conventions:
+ *
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every function returns an int: 0 = RB_OK, <0 = rb_status, >0 = a cudaError_t. Nothing throws.
+ *   - `rb_*` device entry points take DEVICE pointers owned by the caller, an explicit stream
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream) and a caller-provided device
+ *     workspace; they launch asynchronously, never allocate and never synchronise.
+ *   - `rb_ctx_*` / `rb_process_host` take HOST pointers and own their device scratch, pinned staging
+ *     and stream; they return after the results are in the host output buffer.
+ *   - there is no CPU fallback anywhere: without a CUDA device every call fails loudly.
+ *
+ * Layout. A batch is B utterances stored as rows of a [B, ld] float32 matrix (row stride `ld` elements,
+ * ld % 4 == 0, base pointer 16-byte aligned); utterance u uses the first len[u] <= ld samples of its row,
+ * the rest is ignored on input and left untouched on output. Ragged per-utterance data is CSR: an int32
+ * offset array with one more entry than there are owners, and a packed value array.
+ *
+ * Random parameters are NOT drawn here. The host draws them with the reference's own numpy calls, in the
+ * reference's order (RawBoost.py:15,79,80,90), so both sides see identical filter taps and impulse
+ * positions; this library only does the arithmetic.
+ */
+#ifndef RAWBOOST_B200_H_
+#define RAWBOOST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RB_API __attribute__((visibility("default")))
+#else
+#define RB_API
+#endif
+
+typedef enum rb_status {
+  RB_OK = 0,
+  RB_ERR_INVALID_ARG = -1,   /* null pointer, negative size, unknown algo ...            */
+  RB_ERR_ALIGNMENT = -2,     /* ld % 4 != 0 or a waveform pointer not 16-byte aligned     */
+  RB_ERR_WORKSPACE = -3,     /* workspace smaller than rb_workspace_bytes()               */
+  RB_ERR_NO_DEVICE = -4,     /* no CUDA device / wrong architecture (needs sm_100)        */
+  RB_ERR_PLAN = -5           /* a plan field required by the requested algo is missing    */
+} rb_status;
+
+/* Human-readable text for a return code of any function below (rb_status or cudaError_t). */
+RB_API const char* rb_error_string(int code);
+RB_API int rb_abi_version(void);
+
+/*
+ * Device-side plan for one batch: everything the reference draws from np.random, already on the device.
+ * Fields an algo does not use may be NULL/0.
+ *
+ *  LnL  (RawBoost.py:59-69)  n_f filters per utterance; filter i of utterance u is applied to x**(i+1).
+ *       lnl_taps      float32[lnl_tap_off[B*n_f]]   taps b (as genNotchCoeffs returns them, RawBoost.py:28-48)
+ *       lnl_tap_off   int32  [B*n_f + 1]            filter (u,i) owns taps [off[u*n_f+i], off[u*n_f+i+1])
+ *  ISD  (RawBoost.py:73-84)
+ *       isd_off       int32  [B + 1]                impulses of utterance u: [off[u], off[u+1])
+ *       isd_idx       int32  [isd_off[B]]           positions p (unique per utterance, < len[u])
+ *       isd_fr        float64[isd_off[B]]           f_r = (2*rand-1)*(2*rand-1), kept in float64 so that ISD on
+ *                                                   float32 input reproduces the reference bit for bit
+ *       g_sd          gain
+ *  SSI  (RawBoost.py:89-97)
+ *       ssi_noise     float32[B, ld]                np.random.normal(0,1,len[u]) per row
+ *       ssi_taps/off  as LnL with one filter per utterance (int32[B+1])
+ *       ssi_snr_db    float32[B]
+ */
+typedef struct rb_plan {
+  int32_t n_f;
+  const float* lnl_taps;
+  const int32_t* lnl_tap_off;
+  const int32_t* isd_off;
+  const int32_t* isd_idx;
+  const double* isd_fr;
+  float g_sd;
+  const float* ssi_noise;
+  const float* ssi_taps;
+  const int32_t* ssi_tap_off;
+  const float* ssi_snr_db;
+} rb_plan;
+
+/* Device workspace (bytes) that rb_* entry points need for a batch of B rows of stride ld. */
+RB_API size_t rb_workspace_bytes(int B, int ld);
+
+/* ---- a-4  filterFIR(x, b)  (RawBoost.py:51-56), batched --------------------------------------------------
+ * y[u][n] = sum_k b_u[k] * x[u][n + (K_u+1)/2 - k],  x == 0 outside [0, len[u]);  any K_u >= 1.
+ * taps float32[tap_off[B]], tap_off int32[B+1]. No workspace. */
+RB_API int rb_filter_fir(const float* x, const int32_t* len, int B, int ld, const float* taps,
+                  const int32_t* tap_off, float* y, void* stream);
+
+/* ---- a-2  normWav(x, always)  (RawBoost.py:20-25), batched ---------------------------------------------
+ * y = x / max|x| if (always || max|x| > 1) else x. Bit-exact with numpy on float32 input. */
+RB_API int rb_normwav(const float* x, const int32_t* len, int B, int ld, int always, float* y, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* ---- a-5  LnL_convolutive_noise  (RawBoost.py:59-69), arithmetic part ----------------------------------
+ * y = normWav(s - mean(s), 0),  s = sum_i filterFIR(x**(i+1), b_i). Uses plan->n_f, lnl_taps, lnl_tap_off. */
+RB_API int rb_lnl(const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y, void* workspace,
+           size_t workspace_bytes, void* stream);
+
+/* ---- a-6  ISD_additive_noise  (RawBoost.py:73-84), arithmetic part -------------------------------------
+ * y = normWav(x with y[p] = x[p] + g_sd*x[p]*f_r at the impulse positions, 0). Bit-exact on float32 input. */
+RB_API int rb_isd(const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y, void* workspace,
+           size_t workspace_bytes, void* stream);
+
+/* ---- a-7  SSI_additive_noise  (RawBoost.py:89-97), arithmetic part -------------------------------------
+ * y = x + filterFIR(noise, b) * ||x||_2 / (||filterFIR(noise, b)||_2 * 10^(snr/20)). */
+RB_API int rb_ssi(const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y, void* workspace,
+           size_t workspace_bytes, void* stream);
+
+/* ---- a-8  process_Rawboost_feature(feature, sr, args, algo)  (asvspoof_2019_augall_3.py:377-439) -------
+ * algo 1 LnL, 2 ISD, 3 SSI, 4 LnL>ISD>SSI, 5 LnL>ISD (fused), 6 LnL>SSI, 7 ISD>SSI, 8 normWav(LnL+ISD);
+ * any other value copies x to y. x and y may alias only for the copy case. */
+RB_API int rb_process(int algo, const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- host-buffer entry point (what a non-torch caller binds; used for the end-to-end measurement) ------
+ * A context owns one stream, pinned staging and device scratch on `device`, grown on demand and reused.
+ * rb_process_host: every pointer (x, len, y and all plan fields) is a HOST pointer; copies host->device,
+ * runs rb_process, copies y back and returns when y is complete. */
+typedef struct rb_ctx rb_ctx;
+RB_API int rb_ctx_create(rb_ctx** out, int device);
+RB_API int rb_ctx_destroy(rb_ctx* ctx);
+RB_API int rb_process_host(rb_ctx* ctx, int algo, const float* x, const int32_t* len, int B, int ld,
+                    const rb_plan* plan, float* y);
+/* bytes moved by the last rb_process_host call: host->device and device->host */
+RB_API int rb_ctx_last_traffic(const rb_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------------------
+ * rb_probe_fp32: runs a register-resident FFMA2 (packed=1) or FFMA (packed=0) chain on every SM and
+ * returns the achieved FLOP count in *flops; the caller times it with events on `stream`.
+ * rb_launch_count: number of kernels this library has launched in this process (all entry points). */
+RB_API int rb_probe_fp32(int packed, int iters, float* sink /* device, >= 1 float */, double* flops, void* stream);
+RB_API uint64_t rb_launch_count(void);
+/* rb_profile_enable(1): bracket every FIR-bank kernel launch (the dominant kernel of algos 1,3,4,5,6,8) with CUDA
+ * events on its launching stream. rb_profile_read: wait for them and return the accumulated device milliseconds and
+ * launch count since the last reset. Off by default; costs two event records per launch when on. */
+RB_API int rb_profile_enable(int on);
+RB_API int rb_profile_read(double* fir_ms, uint64_t* fir_launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAWBOOST_B200_H_ */

@@ -1,0 +1,91 @@
+// Shared constants and small device helpers for the RawBoost sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include "rawboost_b200.h"
+
+namespace rb {
+
+// ---- tiling of the FIR-bank kernel (rb_fir_bank.cu) ------------------------------------------------
+constexpr int kThreads = 128;               // 4 warps per CTA, up to 4 CTAs per SM
+constexpr int kR = 20;                      // consecutive outputs per thread (80 B stride -> conflict-free LDS.128)
+constexpr int kTile = kThreads * kR;        // 2560 outputs per CTA
+constexpr int kWarpSpan = 32 * kR;          // 640 outputs per warp
+constexpr int kWin = kR + 4;                // circular register window (floats)
+constexpr int kBodyTaps = kWin;             // taps consumed per unrolled loop body (6 groups of 4)
+constexpr int kHalo = 256;                  // default staging starts kHalo samples before the tile
+constexpr int kSegTaps = 512;               // longest filter segment handled by one staging
+constexpr int kTapCap = 528;                // staged taps per copy: roundup(3 + 512 + 1, 24)
+constexpr int kXS = kTile + 2 * kHalo + 64; // staged samples (3136)
+constexpr int kMaxReach = kXS - (kThreads - 1) * kR - kWin - kBodyTaps;  // e + Kseg must stay <= this (548)
+
+// ---- per-tile partial statistics written by the FIR-bank and dense-stats kernels --------------------
+// [B][ntiles][kStatN] floats: sum, sum of squares, min, max, min/max over samples NOT hit by an ISD impulse.
+constexpr int kStatN = 8;
+enum { S_SUM = 0, S_SUMSQ = 1, S_MIN = 2, S_MAX = 3, S_MINU = 4, S_MAXU = 5 };
+
+// ---- per-utterance scalars consumed by the dense apply pass: out = ((in - sub) / div1) / div2 -------
+struct __align__(16) UttParams {
+  float sub;    // mean removed by LnL (0 otherwise)
+  float div1;   // first conditional peak normalisation (1 = idle)
+  float div2;   // second one (after ISD)              (1 = idle)
+  float scale;  // SSI: noise gain
+};
+
+inline int tiles_for(int ld) { return (ld + kTile - 1) / kTile; }
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+#define RB_CUDA(expr)                                  \
+  do {                                                 \
+    cudaError_t e__ = (expr);                          \
+    if (e__ != cudaSuccess) return (int)e__;           \
+  } while (0)
+#define RB_LAUNCH_CHECK()                              \
+  do {                                                 \
+    cudaError_t e__ = cudaGetLastError();              \
+    if (e__ != cudaSuccess) return (int)e__;           \
+    ::rb::count_launch();                              \
+  } while (0)
+
+// ---- optional per-launch timing of the FIR-bank kernel (bench.py's roofline figure) ------------------
+// When enabled through rb_profile_enable(), launch_fir_bank brackets its launch with CUDA events recorded on
+// the launching stream; rb_profile_read() synchronises them and returns the accumulated device time.
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st);
+
+// ---- warp / block reductions (shuffle tree, deterministic) -----------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// NaN-propagating max|.| helpers: numpy's amax returns NaN if any element is NaN; fmaxf would drop it.
+__device__ __forceinline__ float nan_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
+__device__ __forceinline__ float nan_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
+
+// ---- kernel launchers shared between translation units (all asynchronous on `st`) ------------------
+// FIR bank: y[u] = sum_f FIR(x[u] ** (pow_base + f*pow_step), taps of filter (u,f)); optional tile stats + ISD mask.
+int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const float* taps, const int32_t* tap_off,
+                    int n_f, int pow_base, int pow_step, float* y, float* stats /*nullable*/,
+                    const uint32_t* mask /*nullable*/, int mask_ld, cudaStream_t st);
+
+}  // namespace rb

@@ -1,0 +1,277 @@
+// rb_fir_bank.cu -- batched bank of ragged-length FIR filters over successive powers of a waveform.
+//
+// Replaces the arithmetic of filterFIR (/root/reference/datautils/RawBoost.py:51-56) and of the loop body of
+// LnL_convolutive_noise (RawBoost.py:61-66):
+//
+//     y[u][n] = sum_f  sum_k  b_{u,f}[k] * x[u][n + (K_{u,f}+1)/2 - k] ** (pow_base + f*pow_step)
+//
+// with x == 0 outside [0, len[u]). This is a direct convolution on the FP32 pipe (not a dense contraction, so
+// no tensor cores). Design, B200 (sm_100a):
+//
+//  * One CTA (128 threads) owns a tile of 2560 consecutive outputs of one utterance; each thread owns 20
+//    consecutive outputs and keeps 20 x 2 partial accumulators in registers across ALL filters of the bank,
+//    so the raw sum is written to HBM exactly once.
+//  * The tile plus a 256-sample halo on each side is staged once in shared memory (vectorised, coalesced
+//    float4 loads, zero-filled outside the utterance); the power x**p of the current filter is formed once
+//    per staged sample (in fp64, rounded once, so it tracks numpy's float32 powf), not once per tap.
+//  * Inner loop: register-tiled sliding window. A thread holds a circular window of 24 staged samples in
+//    registers; per group of 4 taps it issues ONE LDS.128 for the 4 new window samples and TWO broadcast
+//    LDS.128 for the taps, then 40 packed FFMA2 (fma.rn.f32x2, sm_100) = 80 FMAs. The 80-byte stride
+//    between threads makes the window LDS.128 bank-conflict-free.
+//  * FFMA2 needs both operands as aligned register pairs. Even outputs pair taps (h[i],h[i+1]) with window
+//    samples (W[m],W[m+1]), m even. Odd outputs would need misaligned window pairs, so they use a second
+//    copy of the taps shifted by one (ho[i] = he[i-1]) against the same aligned window pairs. The two halves
+//    of an accumulator pair hold the even-tap and odd-tap partial sums of one output and are added at the end.
+//  * Taps are zero-padded to a multiple of 24 (the unrolled body) and reversed so the window slides upwards.
+//    Filters longer than 512 taps are processed as segments with their own staging offset.
+//  * Epilogue: per-tile sum / sum of squares / min / max (and min / max over samples not hit by an ISD impulse,
+//    from a per-utterance bit mask) via warp shuffles; outputs go through shared memory so the global store is
+//    a coalesced STG.128 stream.
+#include "rb_common.cuh"
+
+namespace rb {
+
+namespace {
+
+struct __align__(16) FirSmem {
+  float x1[kXS];        // staged samples, x1[j] = x[gbase + j]
+  float xp[kXS];        // x1 ** power of the current filter (also reused to transpose the outputs)
+  float he[kTapCap];    // reversed, zero-padded taps for even outputs
+  float ho[kTapCap];    // the same shifted by one for odd outputs
+  float red[4][kStatN]; // per-warp partial statistics
+};
+
+__device__ __forceinline__ float pow_round_once(float v, int p) {
+  // v**p for small integer p >= 1, evaluated in fp64 and rounded to fp32 once.
+  double d = (double)v, acc = d;
+  for (int i = 1; i < p; ++i) acc *= d;
+  return (float)acc;
+}
+
+// Stage x[gbase .. gbase+kXS) of one utterance row into smem, zero outside [0, len).
+__device__ __forceinline__ void stage_x(float* __restrict__ dst, const float* __restrict__ row, int len, int gbase) {
+  // gbase is a multiple of 4 and the row is 16-byte aligned, so every chunk is an aligned float4.
+  for (int c = threadIdx.x; c < kXS / 4; c += kThreads) {
+    const int pos = gbase + 4 * c;
+    float4 v;
+    if (pos >= 0 && pos + 3 < len) {
+      v = __ldg(reinterpret_cast<const float4*>(row + pos));
+    } else {
+      v.x = (pos + 0 >= 0 && pos + 0 < len) ? __ldg(row + pos + 0) : 0.f;
+      v.y = (pos + 1 >= 0 && pos + 1 < len) ? __ldg(row + pos + 1) : 0.f;
+      v.z = (pos + 2 >= 0 && pos + 2 < len) ? __ldg(row + pos + 2) : 0.f;
+      v.w = (pos + 3 >= 0 && pos + 3 < len) ? __ldg(row + pos + 3) : 0.f;
+    }
+    reinterpret_cast<float4*>(dst)[c] = v;
+  }
+}
+
+// One filter segment: acc[r] += sum_i h[i] * src[t*kR + r + i + e0], taps already staged in he/ho (nbody*24 each).
+__device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __restrict__ src, const float* __restrict__ he,
+                                             const float* __restrict__ ho, int e0, int nbody) {
+  float2 w[kWin / 2];
+  const float4* xq = reinterpret_cast<const float4*>(src + threadIdx.x * kR + e0);
+#pragma unroll
+  for (int m = 0; m < kR / 4; ++m) {
+    const float4 v = xq[m];
+    w[2 * m] = make_float2(v.x, v.y);
+    w[2 * m + 1] = make_float2(v.z, v.w);
+  }
+  xq += kR / 4;
+  const float4* pe = reinterpret_cast<const float4*>(he);
+  const float4* po = reinterpret_cast<const float4*>(ho);
+  for (int body = 0; body < nbody; ++body) {
+#pragma unroll
+    for (int g = 0; g < kWin / 4; ++g) {
+      // the chunk that completes the window of this group lands in the slot freed by the previous group
+      const float4 v = *xq++;
+      w[((kR + 4 * g) % kWin) / 2] = make_float2(v.x, v.y);
+      w[((kR + 4 * g) % kWin) / 2 + 1] = make_float2(v.z, v.w);
+      const float4 e = *pe++;
+      const float4 o = *po++;
+      const float2 e01 = make_float2(e.x, e.y), e23 = make_float2(e.z, e.w);
+      const float2 o01 = make_float2(o.x, o.y), o23 = make_float2(o.z, o.w);
+#pragma unroll
+      for (int r = 0; r < kR; r += 2) {
+        const float2 wa = w[((4 * g + r) % kWin) / 2];
+        const float2 wb = w[((4 * g + r + 2) % kWin) / 2];
+        acc[r] = __ffma2_rn(e01, wa, acc[r]);          // even output r   : taps 4g+0,1 x W[r],  W[r+1]
+        acc[r] = __ffma2_rn(e23, wb, acc[r]);          //                   taps 4g+2,3 x W[r+2],W[r+3]
+        acc[r + 1] = __ffma2_rn(o01, wa, acc[r + 1]);  // odd output r+1  : shifted taps, same window pairs
+        acc[r + 1] = __ffma2_rn(o23, wb, acc[r + 1]);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, const float* __restrict__ taps,
+                const int32_t* __restrict__ tap_off, int n_f, int pow_base, int pow_step, float* __restrict__ y,
+                float* __restrict__ stats, const uint32_t* __restrict__ mask, int mask_ld) {
+  __shared__ FirSmem sm;
+  const int u = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int ntiles = gridDim.x;
+  const int len = len_arr[u];
+  const int tile0 = tile * kTile;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  float* st_out = stats ? stats + ((size_t)u * ntiles + tile) * kStatN : nullptr;
+
+  if (tile0 >= len) {  // tile entirely past the end of this utterance: neutral statistics, nothing else
+    if (st_out && tid < kStatN) {
+      float v = 0.f;
+      if (tid == S_MIN || tid == S_MINU) v = INFINITY;
+      if (tid == S_MAX || tid == S_MAXU) v = -INFINITY;
+      st_out[tid] = v;
+    }
+    return;
+  }
+  const float* row = x + (size_t)u * ld;
+  const bool warp_active = tile0 + warp * kWarpSpan < len;  // warps whose outputs are all past the end only help staging
+
+  int gbase = tile0 - kHalo;
+  stage_x(sm.x1, row, len, gbase);
+
+  float2 acc[kR];
+#pragma unroll
+  for (int r = 0; r < kR; ++r) acc[r] = make_float2(0.f, 0.f);
+
+  int staged_pow = 1;  // power currently held by sm.xp (1 = none, x1 is used directly)
+  for (int f = 0; f < n_f; ++f) {
+    const int t0 = tap_off[u * n_f + f];
+    const int K = tap_off[u * n_f + f + 1] - t0;
+    if (K <= 0) continue;
+    const int power = pow_base + f * pow_step;
+    const int shift = (K + 1) >> 1;  // reference delay compensation, RawBoost.py:52,55
+    for (int i0 = 0; i0 < K; i0 += kSegTaps) {
+      const int kseg = min(kSegTaps, K - i0);
+      // reversed taps h[m] = b[K-1-m]; this segment covers m in [i0, i0+kseg):
+      //   y[n] += sum_{i<kseg} h[i0+i] * xp[n + i + d],  d = shift - (K-1) + i0
+      const int d = shift - (K - 1) + i0;
+      int e = tile0 + d - gbase;
+      __syncthreads();  // previous segment done with he/ho/xp (and x1 staged on first pass)
+      if (e < 0 || e + kseg > kMaxReach) {  // uniform: restage the samples around this segment
+        gbase = (tile0 + d) & ~3;
+        e = tile0 + d - gbase;
+        stage_x(sm.x1, row, len, gbase);
+        staged_pow = 1;
+        __syncthreads();
+      }
+      const int z = e & 3;                                      // leading zero taps that align the window to 16 B
+      const int nbody = (z + kseg + 1 + kBodyTaps - 1) / kBodyTaps;
+      for (int i = tid; i < nbody * kBodyTaps; i += kThreads) {
+        const int m = i - z;                                    // he[i] = h[i0 + m]
+        const float hv = (m >= 0 && m < kseg) ? __ldg(taps + t0 + (K - 1 - (i0 + m))) : 0.f;
+        sm.he[i] = hv;
+        if (i + 1 < nbody * kBodyTaps) sm.ho[i + 1] = hv;
+        if (i == 0) sm.ho[0] = 0.f;
+      }
+      const float* src = sm.x1;
+      if (power != 1) {
+        if (staged_pow != power) {
+          for (int j = tid; j < kXS; j += kThreads) sm.xp[j] = pow_round_once(sm.x1[j], power);
+          staged_pow = power;
+        }
+        src = sm.xp;
+      }
+      __syncthreads();
+      if (warp_active) conv_segment(acc, src, sm.he, sm.ho, e - z, nbody);
+    }
+  }
+  __syncthreads();  // everyone is done reading xp; reuse it to transpose the outputs
+
+  // ---- epilogue: fold the accumulator halves, statistics, coalesced store ---------------------------
+  const int n0 = tile0 + tid * kR;
+  float s_sum = 0.f, s_sq = 0.f, s_min = INFINITY, s_max = -INFINITY, s_minu = INFINITY, s_maxu = -INFINITY;
+  uint32_t hit = 0;  // bit r set: output n0+r is an ISD impulse position
+  if (mask && n0 < len) {
+    const uint32_t* mrow = mask + (size_t)u * mask_ld;
+    const int wi = n0 >> 5, sh = n0 & 31;
+    uint32_t lo = mrow[wi];
+    uint32_t hi = (sh > 32 - kR && wi + 1 < mask_ld) ? mrow[wi + 1] : 0u;
+    hit = (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+  }
+  float outv[kR];
+#pragma unroll
+  for (int r = 0; r < kR; ++r) {
+    const float v = acc[r].x + acc[r].y;
+    outv[r] = v;
+    if (n0 + r < len) {
+      s_sum += v;
+      s_sq = fmaf(v, v, s_sq);
+      s_min = fminf(s_min, v);
+      s_max = fmaxf(s_max, v);
+      if (!((hit >> r) & 1u)) {
+        s_minu = fminf(s_minu, v);
+        s_maxu = fmaxf(s_maxu, v);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < kR / 4; ++m)
+    reinterpret_cast<float4*>(sm.xp + tid * kR)[m] = make_float4(outv[4 * m], outv[4 * m + 1], outv[4 * m + 2], outv[4 * m + 3]);
+
+  if (stats) {
+    s_sum = warp_sum(s_sum);
+    s_sq = warp_sum(s_sq);
+    s_min = warp_min(s_min);
+    s_max = warp_max(s_max);
+    s_minu = warp_min(s_minu);
+    s_maxu = warp_max(s_maxu);
+    if (lane == 0) {
+      sm.red[warp][S_SUM] = s_sum;
+      sm.red[warp][S_SUMSQ] = s_sq;
+      sm.red[warp][S_MIN] = s_min;
+      sm.red[warp][S_MAX] = s_max;
+      sm.red[warp][S_MINU] = s_minu;
+      sm.red[warp][S_MAXU] = s_maxu;
+    }
+  }
+  __syncthreads();
+  if (stats && tid < kStatN) {
+    float v;
+    if (tid == S_SUM || tid == S_SUMSQ) v = (sm.red[0][tid] + sm.red[1][tid]) + (sm.red[2][tid] + sm.red[3][tid]);
+    else if (tid == S_MIN || tid == S_MINU) v = fminf(fminf(sm.red[0][tid], sm.red[1][tid]), fminf(sm.red[2][tid], sm.red[3][tid]));
+    else if (tid == S_MAX || tid == S_MAXU) v = fmaxf(fmaxf(sm.red[0][tid], sm.red[1][tid]), fmaxf(sm.red[2][tid], sm.red[3][tid]));
+    else v = 0.f;
+    st_out[tid] = v;
+  }
+  float* yrow = y + (size_t)u * ld + tile0;
+  const int valid = min(kTile, len - tile0);
+#pragma unroll
+  for (int k = 0; k < kR / 4; ++k) {
+    const int c = k * kThreads + tid;  // float4 chunk within the tile
+    const int p = 4 * c;
+    if (p + 3 < valid) {
+      reinterpret_cast<float4*>(yrow)[c] = reinterpret_cast<const float4*>(sm.xp)[c];
+    } else {
+      for (int q = 0; q < 4; ++q)
+        if (p + q < valid) yrow[p + q] = sm.xp[p + q];
+    }
+  }
+}
+
+}  // namespace
+
+int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const float* taps, const int32_t* tap_off,
+                    int n_f, int pow_base, int pow_step, float* y, float* stats, const uint32_t* mask, int mask_ld,
+                    cudaStream_t st) {
+  if (B <= 0 || ld <= 0) return RB_OK;
+  // gridDim.y is limited to 65535: split very large batches over several launches.
+  const int ntiles = tiles_for(ld);
+  for (int b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = min(65535, B - b0);
+    dim3 grid(ntiles, nb);
+    profile_begin(st);
+    fir_bank_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)b0 * ld, len + b0, ld, taps, tap_off + (size_t)b0 * n_f, n_f,
+                                                pow_base, pow_step, y + (size_t)b0 * ld,
+                                                stats ? stats + (size_t)b0 * ntiles * kStatN : nullptr,
+                                                mask ? mask + (size_t)b0 * mask_ld : nullptr, mask_ld);
+    profile_end(st);
+    RB_LAUNCH_CHECK();
+  }
+  return RB_OK;
+}
+
+}  // namespace rb

@@ -1,0 +1,198 @@
+"""Batched device execution of RawBoost plans through the C ABI.
+
+PyTorch is plumbing only here (device memory, streams, pinned buffers); all arithmetic happens in
+``lib/librawboost_b200.so``. There is no CPU fallback: constructing an :class:`Engine` without CUDA raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .plans import BatchPlan, padded_ld
+
+
+@dataclass
+class DevicePlan:
+    """A :class:`BatchPlan` whose arrays live on the device; ``struct`` is the ``rb_plan`` passed to the ABI."""
+    B: int
+    ld: int
+    lengths: torch.Tensor
+    tensors: dict
+    struct: _lib.RbPlan
+    host: Optional[BatchPlan] = None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One engine per (process, device). Owns a growable device workspace; thread-compatible, not thread-safe."""
+
+    def __init__(self, device: int | str | torch.device = 0):
+        if not torch.cuda.is_available():
+            raise _lib.RawBoostLibraryError("rawboost_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        major, _ = torch.cuda.get_device_capability(self.device)
+        if major != 10:
+            raise _lib.RawBoostLibraryError(f"rawboost_b200 is built for sm_100a only; device capability is {major}.x")
+        self._ws: Optional[torch.Tensor] = None
+        self._ctx = None
+
+    # -- memory ---------------------------------------------------------------------------------------
+    def workspace(self, B: int, ld: int) -> torch.Tensor:
+        need = int(self.lib.rb_workspace_bytes(B, ld))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    @staticmethod
+    def _ws_ptr(ws: torch.Tensor) -> int:
+        return (ws.data_ptr() + 255) // 256 * 256
+
+    def upload_plan(self, plan: BatchPlan, non_blocking: bool = True) -> DevicePlan:
+        """Copy the CSR arrays of a host plan to the device (pinned staging when available)."""
+        t = {}
+        for name in ("lnl_taps", "lnl_tap_off", "isd_off", "isd_idx", "isd_fr", "ssi_noise", "ssi_taps", "ssi_tap_off", "ssi_snr_db"):
+            arr = getattr(plan, name)
+            if arr is not None:
+                src = torch.from_numpy(np.ascontiguousarray(arr))
+                t[name] = src.to(self.device, non_blocking=False)
+            else:
+                t[name] = None
+        lengths = torch.from_numpy(np.ascontiguousarray(plan.lengths)).to(self.device)
+        s = _lib.RbPlan()
+        s.n_f = int(plan.n_f)
+        s.g_sd = float(plan.g_sd)
+        for name, v in t.items():
+            setattr(s, name, None if v is None else v.data_ptr())
+        return DevicePlan(B=plan.B, ld=plan.ld, lengths=lengths, tensors=t, struct=s, host=plan)
+
+    def pack_waveforms(self, waves: Sequence[np.ndarray], ld: Optional[int] = None):
+        """Host list of 1-D float arrays -> ([B, ld] float32 device tensor, int32 lengths on device)."""
+        lengths = np.array([int(w.shape[0]) for w in waves], dtype=np.int32)
+        ld = ld or padded_ld(int(lengths.max()) if len(waves) else 0)
+        host = np.zeros((len(waves), ld), dtype=np.float32)
+        for u, w in enumerate(waves):
+            host[u, :lengths[u]] = np.asarray(w, dtype=np.float32)
+        return torch.from_numpy(host).to(self.device), torch.from_numpy(lengths).to(self.device)
+
+    # -- execution ------------------------------------------------------------------------------------
+    def process(self, algo: int, x: torch.Tensor, lengths: torch.Tensor, plan: Optional[DevicePlan],
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``process_Rawboost_feature`` for a whole batch on the device: x [B, ld] float32 -> new [B, ld] tensor.
+
+        Asynchronous on torch's current stream. Samples beyond ``lengths[u]`` of the output row are zero when the
+        tensor is allocated here, untouched when ``out`` is passed."""
+        self._check_batch(x, lengths)
+        B, ld = x.shape
+        if out is None:
+            out = torch.zeros_like(x)
+        ws = self.workspace(B, ld)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ps = C.byref(plan.struct) if plan is not None else None
+        with torch.cuda.device(self.device):
+            rc = self.lib.rb_process(int(algo), _ptr(x), _ptr(lengths), B, ld, ps, _ptr(out), C.c_void_p(self._ws_ptr(ws)),
+                                     ws.numel() - 256, C.c_void_p(stream))
+        _lib.check(rc, f"rb_process(algo={algo})")
+        return out
+
+    def filter_fir(self, x: torch.Tensor, lengths: torch.Tensor, taps: torch.Tensor, tap_off: torch.Tensor,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self._check_batch(x, lengths)
+        B, ld = x.shape
+        if out is None:
+            out = torch.zeros_like(x)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.rb_filter_fir(_ptr(x), _ptr(lengths), B, ld, _ptr(taps), _ptr(tap_off), _ptr(out), C.c_void_p(stream))
+        _lib.check(rc, "rb_filter_fir")
+        return out
+
+    def normwav(self, x: torch.Tensor, lengths: torch.Tensor, always: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self._check_batch(x, lengths)
+        B, ld = x.shape
+        if out is None:
+            out = torch.zeros_like(x)
+        ws = self.workspace(B, ld)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.rb_normwav(_ptr(x), _ptr(lengths), B, ld, int(bool(always)), _ptr(out), C.c_void_p(self._ws_ptr(ws)),
+                                     ws.numel() - 256, C.c_void_p(stream))
+        _lib.check(rc, "rb_normwav")
+        return out
+
+    def _check_batch(self, x: torch.Tensor, lengths: torch.Tensor) -> None:
+        if x.device != self.device or lengths.device != self.device:
+            raise ValueError(f"tensors must live on {self.device}")
+        if x.dtype != torch.float32 or x.dim() != 2 or not x.is_contiguous():
+            raise ValueError("x must be a contiguous [B, ld] float32 tensor")
+        if lengths.dtype != torch.int32 or lengths.numel() != x.shape[0]:
+            raise ValueError("lengths must be int32 [B]")
+
+    # -- host-buffer path (rb_process_host): what a non-torch caller of the C ABI would use ---------------
+    def process_host(self, algo: int, x: np.ndarray, plan: Optional[BatchPlan], out: Optional[np.ndarray] = None) -> np.ndarray:
+        """x: [B, ld] float32 host array (pinned for asynchronous DMA); plan: host :class:`BatchPlan`.
+        Copies in, computes, copies out; returns when ``out`` is complete."""
+        if self._ctx is None:
+            ctx = C.c_void_p()
+            _lib.check(self.lib.rb_ctx_create(C.byref(ctx), self.device.index or 0), "rb_ctx_create")
+            self._ctx = ctx
+        if x.dtype != np.float32 or x.ndim != 2 or not x.flags.c_contiguous:
+            raise ValueError("x must be a C-contiguous [B, ld] float32 array")
+        B, ld = x.shape
+        if out is None:
+            out = np.zeros_like(x)
+        s = _lib.RbPlan()
+        keep = []
+        lengths = plan.lengths if plan is not None else np.full(B, ld, dtype=np.int32)
+        if plan is not None:
+            s.n_f = int(plan.n_f)
+            s.g_sd = float(plan.g_sd)
+            for name in ("lnl_taps", "lnl_tap_off", "isd_off", "isd_idx", "isd_fr", "ssi_noise", "ssi_taps", "ssi_tap_off", "ssi_snr_db"):
+                arr = getattr(plan, name)
+                if arr is not None:
+                    arr = np.ascontiguousarray(arr)
+                    keep.append(arr)
+                    setattr(s, name, arr.ctypes.data)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        rc = self.lib.rb_process_host(self._ctx, int(algo), C.c_void_p(x.ctypes.data), C.c_void_p(lengths.ctypes.data), B, ld,
+                                      C.byref(s), C.c_void_p(out.ctypes.data))
+        _lib.check(rc, f"rb_process_host(algo={algo})")
+        return out
+
+    def last_host_traffic(self):
+        h2d, d2h = C.c_uint64(0), C.c_uint64(0)
+        if self._ctx is not None:
+            _lib.check(self.lib.rb_ctx_last_traffic(self._ctx, C.byref(h2d), C.byref(d2h)))
+        return int(h2d.value), int(d2h.value)
+
+    def close(self):
+        if self._ctx is not None:
+            self.lib.rb_ctx_destroy(self._ctx)
+            self._ctx = None
+        self._ws = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default: dict = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine used by the per-utterance reference-style functions in :mod:`RawBoost`."""
+    eng = _default.get(device)
+    if eng is None:
+        eng = _default[device] = Engine(device)
+    return eng

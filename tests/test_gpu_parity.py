@@ -1,0 +1,291 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the reference's golden outputs.
+
+Tolerances (BASELINE.json north_star): integer work bit-exact; ISD / normWav on float32 input bit-exact; every
+FIR-based result max-abs <= 1e-5 against the float64 oracle on peak-normalised scale.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import rawboost_oracle as orc  # noqa: E402  (checker only)
+
+TOL = 1e-5
+ARGS = orc.make_args()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from scl_deepfake_audio_detection_b200.engine import Engine
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return Engine(0)
+
+
+@pytest.fixture(scope="module")
+def P():
+    from scl_deepfake_audio_detection_b200 import plans
+    return plans
+
+
+def run_batch(eng, P, algo, waves, seeds, args=ARGS):
+    """Draw plans (host, reference stream order), run the whole batch on the device, return per-utterance arrays."""
+    bp = P.draw_batch([w.shape[0] for w in waves], 16000, args, algo, seeds=seeds)
+    x, ln = eng.pack_waveforms(waves, ld=bp.ld)
+    dp = eng.upload_plan(bp)
+    y = eng.process(algo, x, ln, dp)
+    torch.cuda.synchronize()
+    y = y.cpu().numpy()
+    return [y[u, :w.shape[0]] for u, w in enumerate(waves)], bp
+
+
+def oracle_batch(algo, waves, seeds, args=ARGS):
+    out = []
+    for w, s in zip(waves, seeds):
+        np.random.seed(int(s))
+        out.append(np.asarray(orc.process(w, 16000, args, algo)))
+    return out
+
+
+def max_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b))) if a.size else 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# operators
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K", [1, 2, 3, 4, 11, 64, 491])
+def test_filter_fir_golden(eng, golden, K):
+    arrays, _ = golden
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    x, b, ref = arrays[f"fir_x_K{K}"], arrays[f"fir_b_K{K}"], arrays[f"fir_y_K{K}"]
+    y = rb.filterFIR(x, b)
+    assert y.dtype == np.float32 and y.shape == ref.shape
+    assert max_err(y, ref) <= TOL * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("K,L", [(513, 3000), (700, 9000), (1500, 5200), (2049, 2600), (491, 1), (7, 2561), (24, 2560)])
+def test_filter_fir_long_and_edge(eng, K, L):
+    """Filters longer than one staged segment (512 taps) and tile-boundary lengths."""
+    rs = np.random.RandomState(K * 7 + L)
+    x = rs.standard_normal(L).astype(np.float32)
+    b = rs.standard_normal(K) / np.sqrt(K)
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    y = rb.filterFIR(x, b)
+    ref = orc.filter_fir_closed_form(x, b.astype(np.float32))
+    assert max_err(y, ref) <= TOL * max(1.0, np.abs(ref).max())
+    assert max_err(orc.filter_fir(x, b), ref) <= 1e-6  # the closed form is the reference formula
+
+
+def test_filter_fir_linearity_full_size(eng):
+    """Size-independent property at BASELINE size: FIR(a*x1 + x2) == a*FIR(x1) + FIR(x2) (to fp32 rounding)."""
+    B, L = 64, 64600
+    rs = np.random.RandomState(1)
+    x1 = rs.uniform(-1, 1, (B, L)).astype(np.float32)
+    x2 = rs.uniform(-1, 1, (B, L)).astype(np.float32)
+    np.random.seed(3)
+    taps = [orc.draw_notch_taps(5, 20, 8000, 100, 1000, 10, 100, 0, 0, 16000).astype(np.float32) for _ in range(B)]
+    off = np.concatenate([[0], np.cumsum([t.shape[0] for t in taps])]).astype(np.int32)
+    td = torch.from_numpy(np.concatenate(taps)).cuda()
+    od = torch.from_numpy(off).cuda()
+    ln = torch.full((B,), L, dtype=torch.int32, device="cuda")
+    f = lambda a: eng.filter_fir(torch.from_numpy(a).cuda(), ln, td, od).cpu().numpy()
+    lhs = f((0.5 * x1 + x2).astype(np.float32))
+    rhs = 0.5 * f(x1) + f(x2)
+    assert max_err(lhs, rhs) <= 2e-6 * max(1.0, np.abs(rhs).max())
+    # spot-check three rows against the oracle
+    for u in (0, 31, 63):
+        assert max_err(f(x1)[u], orc.filter_fir_closed_form(x1[u], taps[u])) <= TOL
+
+
+def test_normwav_bit_exact(eng, golden):
+    arrays, _ = golden
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    for tag in ("quiet", "loud"):
+        x = arrays[f"norm_x_{tag}"]
+        for always in (0, 1):
+            y = rb.normWav(x, always)
+            assert y.dtype == np.float32
+            assert np.array_equal(y, arrays[f"norm_y{always}_{tag}"]), (tag, always)
+    x = arrays["norm_x_quiet"]
+    assert rb.normWav(x, 0) is x
+    y = rb.normWav(arrays["norm_x_loud"], 0)
+    assert np.array_equal(rb.normWav(y, 0), y)  # idempotent once the peak is 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# dispatcher vs the reference's golden outputs (small) and the oracle (full size)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", list(range(0, 9)))
+def test_dispatcher_matches_reference_golden(eng, golden, algo):
+    arrays, meta = golden
+    from conftest import stream_digest
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    for loud in (0, 1):
+        for u in (0, 1):
+            key = f"algo{algo}_loud{loud}_u{u}"
+            x = orc.synth_utterance(u, 16000, bool(loud))
+            x0 = x.copy()
+            np.random.seed(orc.seed_for(u))
+            y = rb.process_Rawboost_feature(x, 16000, ARGS, algo)
+            assert stream_digest() == meta["cases"][key]["stream"], f"{key}: RNG stream diverged from the reference"
+            assert np.array_equal(x, x0), "input mutated"
+            ref = arrays[key]
+            assert y.shape == ref.shape
+            if algo == 0:
+                assert y is x
+            elif algo == 2:
+                assert y.dtype == np.float32 and np.array_equal(y, ref), f"{key}: ISD must be bit-exact on float32 input"
+            else:
+                assert y.dtype == np.float32
+                assert max_err(y, ref) <= TOL, f"{key}: max-abs {max_err(y, ref):.3e}"
+
+
+def test_ragged_batch_matches_oracle_and_golden(eng, P, golden):
+    arrays, _ = golden
+    lens = [1, 2, 37, 600, 4097, 2560, 2561, 16000]
+    waves = [orc.synth_utterance(7, L, False) for L in lens]
+    seeds = [orc.seed_for(7)] * len(lens)
+    got, _ = run_batch(eng, P, 5, waves, seeds)
+    want = oracle_batch(5, waves, seeds)
+    for L, g, w in zip(lens, got, want):
+        assert g.shape == (L,)
+        assert max_err(g, w) <= TOL, f"L={L}: {max_err(g, w):.3e}"
+        key = f"ragged_algo5_L{L}"
+        if key in arrays.files:
+            assert max_err(g, arrays[key]) <= TOL
+
+
+@pytest.mark.parametrize("algo", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_full_length_batch_matches_oracle(eng, P, golden, algo):
+    """64600-sample utterances, both amplitude variants, in one batch; also the reference's own summaries."""
+    _, meta = golden
+    us = [0, 3, 5, 0, 3, 5]
+    loud = [0, 0, 0, 1, 1, 1]
+    waves = [orc.synth_utterance(u, 64600, bool(l)) for u, l in zip(us, loud)]
+    seeds = [orc.seed_for(u) for u in us]
+    got, _ = run_batch(eng, P, algo, waves, seeds)
+    want = oracle_batch(algo, waves, seeds)
+    for u, l, g, w in zip(us, loud, got, want):
+        if algo == 2:
+            assert np.array_equal(g, w), "ISD must be bit-exact on float32 input"
+        else:
+            assert max_err(g, w) <= TOL, f"algo {algo} u{u} loud{l}: {max_err(g, w):.3e}"
+        key = f"algo{algo}_loud{l}_u{u}"
+        if key in meta["full"]:
+            s = meta["full"][key]
+            assert max_err(g[np.array(s["probe_idx"])], s["probe_val"]) <= TOL
+            assert abs(float(np.abs(g.astype(np.float64)).max()) - max(abs(s["min"]), abs(s["max"]))) <= TOL
+
+
+def test_isd_indices_are_integer_exact(eng, P):
+    """The samples ISD changes are exactly the drawn permutation prefix (quiet input: no rescaling)."""
+    x = orc.synth_utterance(11, 64600, False)
+    np.random.seed(orc.seed_for(11))
+    plan = orc.draw_isd_plan(64600, 10)
+    got, bp = run_batch(eng, P, 2, [x], [orc.seed_for(11)])
+    assert np.array_equal(bp.isd_idx, plan.idx.astype(np.int32)) and bp.isd_off.tolist() == [0, plan.idx.shape[0]]
+    changed = np.flatnonzero(got[0] != x)
+    assert set(changed.tolist()) <= set(plan.idx.tolist())       # nothing outside the drawn positions moves
+    assert changed.shape[0] >= plan.idx.shape[0] - 8             # (a gain can round to a no-op on a tiny sample)
+    np.random.seed(orc.seed_for(11))
+    assert np.array_equal(got[0], orc.isd(x, 10, 2))
+
+
+def test_algo5_properties_at_config_size(eng, P):
+    """BASELINE config 3 shape (algo 5, 64600 samples) at a batch the oracle cannot cover: size-independent checks."""
+    B = 256
+    waves = [orc.synth_utterance(u, 64600, bool(u % 2)) for u in range(B)]
+    seeds = [orc.seed_for(u) for u in range(B)]
+    got, bp = run_batch(eng, P, 5, waves, seeds)
+    got1, _ = run_batch(eng, P, 1, waves, seeds)  # same seeds -> same LnL taps
+    for u in range(B):
+        y5, y1 = got[u], got1[u]
+        assert np.all(np.isfinite(y5)) and np.abs(y5).max() <= 1.0 + 1e-6
+        assert np.abs(y1).max() <= 1.0 + 1e-6
+        idx = bp.isd_idx[bp.isd_off[u]:bp.isd_off[u + 1]]
+        untouched = np.ones(64600, dtype=bool)
+        untouched[idx] = False
+        peak = np.abs(y5).max()
+        # untouched samples are the LnL output up to the one common ISD rescale (a divisor >= 1)
+        ratio = np.abs(y1[untouched]).max() / max(np.abs(y5[untouched]).max(), 1e-30)
+        assert ratio >= 1.0 - 1e-6
+        np.testing.assert_allclose(y5[untouched] * ratio, y1[untouched], rtol=0, atol=2e-6)
+        if ratio > 1.0 + 1e-6:
+            assert abs(peak - 1.0) <= 1e-6  # rescaled => the new peak is exactly 1
+    # spot-check a few utterances against the oracle
+    for u in (0, 1, 100, 255):
+        np.random.seed(seeds[u])
+        assert max_err(got[u], orc.process(waves[u], 16000, ARGS, 5)) <= TOL
+    # determinism: same plan, same bits
+    again, _ = run_batch(eng, P, 5, waves[:8], seeds[:8])
+    for u in range(8):
+        assert np.array_equal(again[u], got[u])
+
+
+def test_host_entry_point_equals_device_path(eng, P):
+    waves = [orc.synth_utterance(u, 64600, bool(u % 2)) for u in range(4)]
+    seeds = [orc.seed_for(u) for u in range(4)]
+    for algo in (1, 3, 5, 7):
+        got, bp = run_batch(eng, P, algo, waves, seeds)
+        xh = np.zeros((4, bp.ld), dtype=np.float32)
+        for u, w in enumerate(waves):
+            xh[u, :w.shape[0]] = w
+        yh = eng.process_host(algo, xh, bp)
+        for u, w in enumerate(waves):
+            assert np.array_equal(yh[u, :w.shape[0]], got[u])
+        h2d, d2h = eng.last_host_traffic()
+        assert d2h == xh.nbytes and h2d >= xh.nbytes
+
+
+def test_nondefault_arguments(eng, P):
+    """Longer cascades (K up to 991 -> two staged segments), more bands, N_f = 3, other ISD / SSI knobs."""
+    args = orc.make_args(nBands=6, maxCoeff=200, N_f=3, P=25, g_sd=3, SNRmin=5, SNRmax=15, minG=-3, maxG=2)
+    waves = [orc.synth_utterance(u, 20000 + 17 * u, bool(u % 2)) for u in range(4)]
+    seeds = [orc.seed_for(40 + u) for u in range(4)]
+    for algo in (4, 5, 8):
+        got, _ = run_batch(eng, P, algo, waves, seeds, args)
+        want = oracle_batch(algo, waves, seeds, args)
+        for g, w in zip(got, want):
+            assert max_err(g, w) <= TOL, f"algo {algo}: {max_err(g, w):.3e}"
+
+
+def test_error_codes(eng):
+    import ctypes as C
+    from scl_deepfake_audio_detection_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(2, 64, device="cuda")
+    y = torch.zeros_like(x)
+    ln = torch.full((2,), 64, dtype=torch.int32, device="cuda")
+    ws = eng.workspace(2, 64)
+    wp = C.c_void_p(eng._ws_ptr(ws))
+    # algo 5 without a plan
+    assert lib.rb_process(5, x.data_ptr(), ln.data_ptr(), 2, 64, None, y.data_ptr(), wp, ws.numel() - 256, None) == -5
+    # ld not a multiple of 4
+    assert lib.rb_process(5, x.data_ptr(), ln.data_ptr(), 2, 63, None, y.data_ptr(), wp, ws.numel() - 256, None) == -2
+    # workspace too small
+    assert lib.rb_process(1, x.data_ptr(), ln.data_ptr(), 2, 64, None, y.data_ptr(), wp, 16, None) == -3
+    # in-place is refused for real algos
+    assert lib.rb_process(1, x.data_ptr(), ln.data_ptr(), 2, 64, None, x.data_ptr(), wp, ws.numel() - 256, None) == -1
+    with pytest.raises(_lib.RawBoostLibraryError):
+        _lib.check(-5, "rb_process")
+    assert lib.rb_launch_count() > 0
+
+
+def test_dropin_patches_loader_namespace(eng):
+    """A stand-in loader module that binds the operator names like the reference loaders do (augall_3.py:10)."""
+    import types
+    from scl_deepfake_audio_detection_b200 import dropin, RawBoost as rb
+    fake = types.ModuleType("fake_loader")
+    for n in dropin.OPERATORS + dropin.DISPATCH:
+        setattr(fake, n, lambda *a, **k: (_ for _ in ()).throw(AssertionError("reference path called")))
+    dropin.patch_loader(fake)
+    x = orc.synth_utterance(2, 8000, False)
+    np.random.seed(5)
+    y = fake.RawBoost12(x, orc.make_args(online_aug=True, aug_dir="/nonexistent"), 16000, audio_path="/a/b.wav")
+    np.random.seed(5)
+    want = orc.process(x, 16000, ARGS, 5)
+    assert max_err(y, want) <= TOL and fake.LnL_convolutive_noise is rb.LnL_convolutive_noise

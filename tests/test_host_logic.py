@@ -1,0 +1,208 @@
+"""CPU-side tests: plan drawing vs the oracle and the reference's stream digests, CSR packing, the C-ABI library's
+exported symbols, loud failure without a GPU, and the sharding helpers under a 2-process gloo group."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, stream_digest
+from oracle import rawboost_oracle as orc
+
+ARGS = orc.make_args()
+
+
+@pytest.fixture(scope="module")
+def P():
+    from scl_deepfake_audio_detection_b200 import plans
+    return plans
+
+
+def test_surface_names_and_signatures():
+    """Same names and argument lists as datautils/RawBoost.py and the loaders' dispatcher."""
+    import inspect
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    want = {
+        "randRange": ["x1", "x2", "integer"],
+        "normWav": ["x", "always"],
+        "genNotchCoeffs": ["nBands", "minF", "maxF", "minBW", "maxBW", "minCoeff", "maxCoeff", "minG", "maxG", "fs"],
+        "filterFIR": ["x", "b"],
+        "LnL_convolutive_noise": ["x", "N_f", "nBands", "minF", "maxF", "minBW", "maxBW", "minCoeff", "maxCoeff", "minG", "maxG",
+                                  "minBiasLinNonLin", "maxBiasLinNonLin", "fs"],
+        "ISD_additive_noise": ["x", "P", "g_sd"],
+        "SSI_additive_noise": ["x", "SNRmin", "SNRmax", "nBands", "minF", "maxF", "minBW", "maxBW", "minCoeff", "maxCoeff", "minG",
+                               "maxG", "fs"],
+        "process_Rawboost_feature": ["feature", "sr", "args", "algo"],
+        "RawBoost12": ["x", "args", "sr", "audio_path"],
+    }
+    for name, params in want.items():
+        assert list(inspect.signature(getattr(rb, name)).parameters) == params, name
+
+
+def test_randrange_and_notch_match_reference_golden(P, golden):
+    arrays, meta = golden
+    r = meta["ops"]["randRange"]
+    np.random.seed(3)
+    f = P.randRange(20, 8000, 0)
+    assert isinstance(f, np.ndarray) and f.shape == (1,) and float(f[0]) == r["float"]
+    assert P.randRange(10, 100, 1) == r["int"]
+    assert float(P.randRange(-5, -20, 0)[0]) == r["reversed"]
+    assert stream_digest() == r["stream"]
+    for u in range(6):
+        np.random.seed(orc.seed_for(u))
+        b = P.genNotchCoeffs(5, 20, 8000, 100, 1000, 10, 100, 0, 0, 16000)
+        assert b.dtype == np.float64 and b.shape[0] == meta["ops"][f"notch_u{u}"]["K"]
+        np.testing.assert_allclose(b, arrays[f"notch_u{u}"], rtol=0, atol=1e-15)
+        assert stream_digest() == meta["ops"][f"notch_u{u}"]["stream"]
+
+
+@pytest.mark.parametrize("algo", list(range(1, 9)))
+def test_plan_draws_leave_the_reference_stream_state(P, golden, algo):
+    """Drawing a plan consumes the global stream exactly as the reference's call does (integer-exact parity)."""
+    _, meta = golden
+    for loud in (0, 1):
+        for u in (0, 1):
+            c = meta["cases"][f"algo{algo}_loud{loud}_u{u}"]
+            np.random.seed(orc.seed_for(u))
+            P.draw_for_algo(c["L"], 16000, ARGS, algo)
+            assert stream_digest() == c["stream"]
+    for key in (k for k in meta["full"] if k.startswith(f"algo{algo}_")):
+        u = int(key.split("_")[2][1:])
+        np.random.seed(orc.seed_for(u))
+        P.draw_for_algo(64600, 16000, ARGS, algo)
+        assert stream_digest() == meta["full"][key]["stream"]
+
+
+def test_plans_equal_oracle_plans(P):
+    np.random.seed(21)
+    p = P.draw_for_algo(64600, 16000, ARGS, 4)
+    np.random.seed(21)
+    q1 = orc.draw_lnl_plan(5, 5, 20, 8000, 100, 1000, 10, 100, 0, 0, 5, 20, 16000)
+    q2 = orc.draw_isd_plan(64600, 10)
+    q3 = orc.draw_ssi_plan(64600, 10, 40, 5, 20, 8000, 100, 1000, 10, 100, 0, 0, 16000)
+    assert all(np.array_equal(a, b) for a, b in zip(p.lnl_taps, q1.taps))
+    assert p.isd_idx.dtype == np.int64 and np.array_equal(p.isd_idx, q2.idx) and np.array_equal(p.isd_fr, q2.f_r)
+    assert np.array_equal(p.ssi_noise, q3.noise) and np.array_equal(p.ssi_taps, q3.taps) and p.ssi_snr_db == q3.snr_db
+
+
+def test_pack_builds_csr(P):
+    lens = [10, 64600, 333]
+    seeds = [5, 6, 7]
+    bp = P.draw_batch(lens, 16000, ARGS, 4, seeds=seeds)
+    assert bp.B == 3 and bp.ld == 64600 and bp.lengths.dtype == np.int32 and bp.lengths.tolist() == lens
+    assert bp.n_f == 5 and bp.lnl_tap_off.shape == (16,) and bp.lnl_tap_off[0] == 0
+    assert bp.lnl_taps.dtype == np.float32 and bp.lnl_taps.shape[0] == bp.lnl_tap_off[-1]
+    k = np.diff(bp.lnl_tap_off)
+    assert np.all(k % 2 == 1) and k.min() >= 51 and k.max() <= 491
+    assert bp.isd_off.tolist()[0] == 0 and bp.isd_idx.dtype == np.int32 and bp.isd_fr.dtype == np.float64
+    for u, n in enumerate(lens):
+        idx = bp.isd_idx[bp.isd_off[u]:bp.isd_off[u + 1]]
+        assert len(set(idx.tolist())) == idx.shape[0] and (idx.size == 0 or (idx.min() >= 0 and idx.max() < n))
+        assert np.all(bp.ssi_noise[u, n:] == 0)
+    assert bp.ssi_noise.shape == (3, 64600) and bp.ssi_snr_db.shape == (3,) and bp.g_sd == 2.0
+    # per-utterance re-seeding makes plans independent of batch composition (sharding invariance)
+    solo = P.draw_batch([64600], 16000, ARGS, 4, seeds=[6])
+    assert np.array_equal(solo.isd_idx, bp.isd_idx[bp.isd_off[1]:bp.isd_off[2]])
+    assert np.array_equal(solo.lnl_taps, bp.lnl_taps[bp.lnl_tap_off[5]:bp.lnl_tap_off[10]])
+    assert bp.fir_flops() == pytest.approx(2.0 * sum(n * (np.diff(bp.lnl_tap_off)[5 * u:5 * u + 5].sum() + np.diff(bp.ssi_tap_off)[u])
+                                                    for u, n in enumerate(lens)))
+
+
+def test_library_exports_every_header_symbol():
+    """The C-ABI library loads and exports exactly what include/rawboost_b200.h declares (no compute calls)."""
+    import ctypes
+    from scl_deepfake_audio_detection_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "rawboost_b200.h")).read()
+    declared = set(re.findall(r"RB_API\s+[\w\s\*]+?\b(rb_\w+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rb_abi_version() == 1
+    assert lib.rb_error_string(0) == b"ok" and b"plan" in lib.rb_error_string(-5)
+    assert lib.rb_workspace_bytes(0, 64600) == 0
+    small, big = lib.rb_workspace_bytes(1, 64600), lib.rb_workspace_bytes(4096, 64600)
+    assert 3 * 64600 * 4 <= small and big >= 4096 * 3 * 64600 * 4 and big < 4096 * 3.2 * 64600 * 4
+    assert ctypes.sizeof(_lib.RbPlan) == 88  # matches the C struct layout on LP64
+    # argument validation happens before any CUDA call, so it is checkable without a device
+    assert lib.rb_process(5, 16, 16, 2, 63, None, 16, 256, 1 << 30, None) == -2
+    assert lib.rb_process(5, None, None, 2, 64, None, None, None, 0, None) == -1
+    assert lib.rb_process(5, None, None, 0, 64, None, None, None, 0, None) == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb, _lib
+    from scl_deepfake_audio_detection_b200.engine import Engine
+    with pytest.raises(_lib.RawBoostLibraryError):
+        Engine(0)
+    x = orc.synth_utterance(0, 1000)
+    for call in (lambda: rb.normWav(x, 1), lambda: rb.filterFIR(x, np.ones(3)), lambda: rb.process_Rawboost_feature(x, 16000, ARGS, 5),
+                 lambda: rb.ISD_additive_noise(x, 10, 2)):
+        with pytest.raises(_lib.RawBoostLibraryError):
+            call()
+    assert rb.process_Rawboost_feature(x, 16000, ARGS, 0) is x  # identity needs no device
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "scl-deepfake-audio-detection_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("SURVEY", ""), f"{f} mentions the oracle"
+
+
+def test_shard_range_partitions():
+    from scl_deepfake_audio_detection_b200.sharding import shard_range
+    for total in (0, 1, 7, 4096, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            rs = [shard_range(total, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == total
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch.distributed as dist
+from scl_deepfake_audio_detection_b200 import sharding, plans
+from oracle import rawboost_oracle as orc
+sharding.init_process_group("gloo")
+rank, _, world = sharding.env_rank_world()
+lo, hi = sharding.shard_range(6, rank, world)
+# each rank draws only its shard's plans; per-utterance seeding makes them identical to a single-process draw
+bp = plans.draw_batch([4000] * (hi - lo), 16000, orc.make_args(), 5, seeds=[orc.seed_for(u) for u in range(lo, hi)])
+full = plans.draw_batch([4000] * 6, 16000, orc.make_args(), 5, seeds=[orc.seed_for(u) for u in range(6)])
+ok = np.array_equal(bp.isd_idx, full.isd_idx[full.isd_off[lo]:full.isd_off[hi]]) and \
+     np.array_equal(bp.lnl_taps, full.lnl_taps[full.lnl_tap_off[5 * lo]:full.lnl_tap_off[5 * hi]])
+sharding.barrier()
+t = sharding.max_over_ranks(1.0 + rank)
+n = sharding.sum_over_ranks(hi - lo)
+assert ok and t == float(world) and n == 6.0, (ok, t, n)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    """world_size-2 gloo job on CPU: shards partition the batch, plans match the single-process draw, timing is MAX-reduced."""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    port = 29000 + os.getpid() % 2000
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out.decode()
