@@ -300,19 +300,22 @@ def gpu_arm(a):
         return dt / steps
 
     e2e_steps = max(1, min(a.steps, a.e2e_steps))
-    e2e_s = sharding.max_over_ranks(e2e_run(e2e_steps, 1), dev)
-    h2d, d2h = eng.last_host_traffic()
-    # copy + kernels only (plans pre-drawn), for the breakdown
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.process_host(algo, x_host.numpy(), bp, out=y_host.numpy())
-    copy_s = sharding.max_over_ranks((time.perf_counter() - t0) / e2e_steps, dev)
-    check = float(np.abs(y_host.numpy()[:, :L]).max())
+    if a.no_e2e:
+        e2e_s, copy_s, h2d, d2h, check = float("nan"), float("nan"), 0, 0, None
+    else:
+        e2e_s = sharding.max_over_ranks(e2e_run(e2e_steps, 1), dev)
+        h2d, d2h = eng.last_host_traffic()
+        # copy + kernels only (plans pre-drawn), for the breakdown
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.process_host(algo, x_host.numpy(), bp, out=y_host.numpy())
+        copy_s = sharding.max_over_ranks((time.perf_counter() - t0) / e2e_steps, dev)
+        check = float(np.abs(y_host.numpy()[:, :L]).max())
 
     # ---- CPU baseline on this box's host cores (N=1 only) -----------------------------------------------
     cpu = None
     pool.close()
-    if world == 1:
+    if world == 1 and not a.no_cpu:
         v, ms, n = run_cpu_arm(algo, L, a.cpu_per_core, cores, 2, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n} utterances per step ({a.cpu_per_core} per core x {cores} cores), 2 timed steps, oracle port of the "
@@ -375,6 +378,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="utterances per GPU per step (BASELINE config 3: 4096)")
     ap.add_argument("--length", type=int, default=64600)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--cpu-per-core", type=int, default=8, help="utterances per host core per CPU-baseline step")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "librawboost_b200.so")
+# RAWBOOST_B200_LIB selects another build of the same ABI (kernel-variant experiments); default is the in-tree build.
+LIB_PATH = os.environ.get("RAWBOOST_B200_LIB") or os.path.join(HERE, "lib", "librawboost_b200.so")
 
 RB_ABI_VERSION = 1
 

@@ -5,15 +5,16 @@ set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 root="$(cd "$here/../.." && pwd)"
 out="$here/../lib"
+name="${RB_LIB_NAME:-librawboost_b200}"   # RB_LIB_NAME / RB_EXTRA_FLAGS: kernel-variant experiments
 mkdir -p "$out"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
-       -Xptxas -v -I"$root/include" -I"$here")
+       -Xptxas -v -I"$root/include" -I"$here" ${RB_EXTRA_FLAGS:-})
 objs=()
 for src in rb_fir_bank rb_dense rb_api rb_probe; do
-  "$NVCC" "${FLAGS[@]}" -c "$here/$src.cu" -o "$out/$src.o" 2> "$out/$src.ptxas.log" || { cat "$out/$src.ptxas.log" >&2; exit 1; }
-  objs+=("$out/$src.o")
+  "$NVCC" "${FLAGS[@]}" -c "$here/$src.cu" -o "$out/$name.$src.o" 2> "$out/$name.$src.ptxas.log" || { cat "$out/$name.$src.ptxas.log" >&2; exit 1; }
+  objs+=("$out/$name.$src.o")
 done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/librawboost_b200.so" "${objs[@]}" -Xcompiler -fPIC
-grep -h -E "Used [0-9]+ registers|spill" "$out"/*.ptxas.log | sort | uniq -c | sort -rn | head -20
-echo "built $out/librawboost_b200.so"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/$name.so" "${objs[@]}" -Xcompiler -fPIC
+grep -h -E "Used [0-9]+ registers|spill" "$out"/$name.*.ptxas.log | sort | uniq -c | sort -rn | head -20
+echo "built $out/$name.so"

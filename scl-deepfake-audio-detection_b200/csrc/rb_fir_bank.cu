@@ -43,9 +43,15 @@ struct __align__(16) FirSmem {
 
 __device__ __forceinline__ float pow_round_once(float v, int p) {
   // v**p for small integer p >= 1, evaluated in fp64 and rounded to fp32 once.
+#ifdef RB_POW_FP32
+  float acc = v;
+  for (int i = 1; i < p; ++i) acc *= v;
+  return acc;
+#else
   double d = (double)v, acc = d;
   for (int i = 1; i < p; ++i) acc *= d;
   return (float)acc;
+#endif
 }
 
 // Stage x[gbase .. gbase+kXS) of one utterance row into smem, zero outside [0, len).
@@ -70,6 +76,19 @@ __device__ __forceinline__ void stage_x(float* __restrict__ dst, const float* __
 __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __restrict__ src, const float* __restrict__ he,
                                              const float* __restrict__ ho, int e0, int nbody) {
   float2 w[kWin / 2];
+#ifdef RB_WIN_LDS64
+  // Window loads as 64-bit pairs: leaves ptxas free to keep every window pair in the register bank class the
+  // accumulators are not in (an LDS.128 pins its four registers to an aligned quad, i.e. alternating classes).
+  const float* xq = src + threadIdx.x * kR + e0;
+  auto lds64 = [](const float* p) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+  };
+#pragma unroll
+  for (int m = 0; m < kR / 2; ++m) w[m] = lds64(xq + 2 * m);
+  xq += kR;
+#else
   const float4* xq = reinterpret_cast<const float4*>(src + threadIdx.x * kR + e0);
 #pragma unroll
   for (int m = 0; m < kR / 4; ++m) {
@@ -78,33 +97,44 @@ __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __r
     w[2 * m + 1] = make_float2(v.z, v.w);
   }
   xq += kR / 4;
+#endif
   const float4* pe = reinterpret_cast<const float4*>(he);
   const float4* po = reinterpret_cast<const float4*>(ho);
   for (int body = 0; body < nbody; ++body) {
 #pragma unroll
     for (int g = 0; g < kWin / 4; ++g) {
       // the chunk that completes the window of this group lands in the slot freed by the previous group
+#ifdef RB_WIN_LDS64
+      w[((kR + 4 * g) % kWin) / 2] = lds64(xq);
+      w[((kR + 4 * g) % kWin) / 2 + 1] = lds64(xq + 2);
+      xq += 4;
+#else
       const float4 v = *xq++;
       w[((kR + 4 * g) % kWin) / 2] = make_float2(v.x, v.y);
       w[((kR + 4 * g) % kWin) / 2 + 1] = make_float2(v.z, v.w);
+#endif
       const float4 e = *pe++;
       const float4 o = *po++;
       const float2 e01 = make_float2(e.x, e.y), e23 = make_float2(e.z, e.w);
       const float2 o01 = make_float2(o.x, o.y), o23 = make_float2(o.z, o.w);
+      // Tap-major order: ten consecutive FFMA2 share the tap operand, so it is served by the operand-reuse cache
+      // and every FFMA2 reads only two register pairs from the register file (three would halve... cost a third cycle).
 #pragma unroll
-      for (int r = 0; r < kR; r += 2) {
-        const float2 wa = w[((4 * g + r) % kWin) / 2];
-        const float2 wb = w[((4 * g + r + 2) % kWin) / 2];
-        acc[r] = __ffma2_rn(e01, wa, acc[r]);          // even output r   : taps 4g+0,1 x W[r],  W[r+1]
-        acc[r] = __ffma2_rn(e23, wb, acc[r]);          //                   taps 4g+2,3 x W[r+2],W[r+3]
-        acc[r + 1] = __ffma2_rn(o01, wa, acc[r + 1]);  // odd output r+1  : shifted taps, same window pairs
-        acc[r + 1] = __ffma2_rn(o23, wb, acc[r + 1]);
-      }
+      for (int r = 0; r < kR; r += 2) acc[r] = __ffma2_rn(e01, w[((4 * g + r) % kWin) / 2], acc[r]);          // taps 4g+0,1 x W[r],W[r+1]
+#pragma unroll
+      for (int r = 0; r < kR; r += 2) acc[r] = __ffma2_rn(e23, w[((4 * g + r + 2) % kWin) / 2], acc[r]);      // taps 4g+2,3 x W[r+2],W[r+3]
+#pragma unroll
+      for (int r = 0; r < kR; r += 2) acc[r + 1] = __ffma2_rn(o01, w[((4 * g + r) % kWin) / 2], acc[r + 1]);  // odd outputs: shifted taps,
+#pragma unroll
+      for (int r = 0; r < kR; r += 2) acc[r + 1] = __ffma2_rn(o23, w[((4 * g + r + 2) % kWin) / 2], acc[r + 1]);  // same window pairs
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 4)
+#ifndef RB_MIN_BLOCKS
+#define RB_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kThreads, RB_MIN_BLOCKS)
 fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, const float* __restrict__ taps,
                 const int32_t* __restrict__ tap_off, int n_f, int pow_base, int pow_step, float* __restrict__ y,
                 float* __restrict__ stats, const uint32_t* __restrict__ mask, int mask_ld) {

@@ -39,6 +39,43 @@ fp32_probe_kernel(int iters, float seed, float* __restrict__ sink) {
   if (s == 123.456f) sink[0] = s;  // keeps the chain alive without a store in the common case
 }
 
+// Operand-pattern probes (packed = 2, 3): how fast FFMA2 runs when its operands come from the register file the way
+// the FIR loop's do. Mode 2: one operand shared by runs of 10 (the tap), one distinct per instruction (the window),
+// one accumulator -- exactly the hot loop's pattern without the shared-memory loads. Mode 3: three distinct pairs.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+fp32_pattern_kernel(int iters, float seed, float* __restrict__ sink) {
+  float2 acc[40], w[12], t[4];
+#pragma unroll
+  for (int i = 0; i < 40; ++i) acc[i] = make_float2(seed + i, seed - i);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) w[i] = make_float2(1.0f + (seed + i + threadIdx.x) * 1e-7f, 1.0f - (seed + i) * 1e-7f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i] = make_float2(seed * 1e-3f + i, seed * -1e-3f - i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+          if (MODE == 2) acc[(q & 1) * 20 + 2 * r + (q >> 1)] = __ffma2_rn(t[q], w[(r + (q >> 1) + k) % 12], acc[(q & 1) * 20 + 2 * r + (q >> 1)]);
+          else acc[q * 10 + r] = __ffma2_rn(acc[(q * 10 + r + 7) % 40], w[(r + q + k) % 12], acc[q * 10 + r]);
+        }
+      }
+    }
+    // rotate the window so the compiler cannot hoist anything
+    const float2 w0 = w[0];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) w[i] = w[i + 1];
+    w[11] = w0;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 40; ++i) s += acc[i].x + acc[i].y;
+  if (s == 123.456f) sink[0] = s;
+}
+
 }  // namespace
 }  // namespace rb
 
@@ -49,6 +86,14 @@ extern "C" int rb_probe_fp32(int packed, int iters, float* sink, double* flops, 
   RB_CUDA(cudaGetDevice(&dev));
   RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int blocks = sms * 8;  // 2048 threads per SM
+  if (packed >= 2) {
+    const int pblocks = sms * 4;  // 4 CTAs x 128 threads per SM, like the FIR kernel
+    if (packed == 2) fp32_pattern_kernel<2><<<pblocks, 128, 0, (cudaStream_t)stream>>>(iters, 0.5f, sink);
+    else fp32_pattern_kernel<3><<<pblocks, 128, 0, (cudaStream_t)stream>>>(iters, 0.5f, sink);
+    RB_LAUNCH_CHECK();
+    if (flops) *flops = 2.0 * 2.0 * 160.0 * (double)iters * 128.0 * (double)pblocks;
+    return RB_OK;
+  }
   if (packed)
     fp32_probe_kernel<true><<<blocks, kProbeThreads, 0, (cudaStream_t)stream>>>(iters, 0.5f, sink);
   else
