@@ -9,14 +9,17 @@ namespace rb {
 
 // ---- tiling of the FIR-bank kernel (rb_fir_bank.cu) ------------------------------------------------
 constexpr int kThreads = 128;               // 4 warps per CTA, up to 4 CTAs per SM
-constexpr int kR = 20;                      // consecutive outputs per thread (80 B stride -> conflict-free LDS.128)
+#ifndef RB_KR
+#define RB_KR 20
+#endif
+constexpr int kR = RB_KR;                   // consecutive outputs per thread (20 -> 80 B stride: conflict-free LDS.128)
 constexpr int kTile = kThreads * kR;        // 2560 outputs per CTA
 constexpr int kWarpSpan = 32 * kR;          // 640 outputs per warp
 constexpr int kWin = kR + 4;                // circular register window (floats)
 constexpr int kBodyTaps = kWin;             // taps consumed per unrolled loop body (6 groups of 4)
 constexpr int kHalo = 256;                  // default staging starts kHalo samples before the tile
 constexpr int kSegTaps = 512;               // longest filter segment handled by one staging
-constexpr int kTapCap = 528;                // staged taps per copy: roundup(3 + 512 + 1, 24)
+constexpr int kTapCap = (3 + kSegTaps + 1 + kBodyTaps - 1) / kBodyTaps * kBodyTaps;  // staged taps per copy (528)
 constexpr int kXS = kTile + 2 * kHalo + 64; // staged samples (3136)
 constexpr int kMaxReach = kXS - (kThreads - 1) * kR - kWin - kBodyTaps;  // e + Kseg must stay <= this (548)
 

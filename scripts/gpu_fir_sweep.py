@@ -37,6 +37,10 @@ for K in (51, 131, 271, 491, 503, 1001):
     taps = torch.randn(B * K, device="cuda") / K
     off = torch.arange(0, B + 1, dtype=torch.int32, device="cuda") * K
     ms = timeit(lambda: eng.filter_fir(x, ln, taps, off, out=y))
+    if K == 271:  # correctness spot-check of this build against numpy (closed form of filterFIR)
+        xs, ts, ys = x[3].cpu().numpy().astype(np.float64), taps[3 * K:4 * K].cpu().numpy().astype(np.float64), y[3].cpu().numpy()
+        ref = np.convolve(xs, ts)[(K + 1) // 2:(K + 1) // 2 + L]
+        print("   max-abs error vs numpy:", float(np.abs(ys - ref).max()))
     print(f"filter_fir K={K:5d}  {ms:8.3f} ms  {2.0 * B * L * K / ms / 1e9:7.2f} TFLOP/s")
 
 args = workload.default_args()
