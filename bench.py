@@ -192,7 +192,8 @@ def gpu_arm(a):
     rank, local_rank, world = sharding.env_rank_world()
     cores = host_cores()
     workers = max(1, cores // max(1, world))
-    pool = workload.PlanPool(workers)  # forked before CUDA is initialised; workers only run numpy/scipy
+    native = a.planner == "native"
+    pool = workload.PlanPool(1 if native else workers)  # forked before CUDA is initialised; workers only run numpy/scipy
 
     import ctypes as C
     import torch
@@ -211,9 +212,23 @@ def gpu_arm(a):
     lengths = [L] * B
 
     # ---- synthetic inputs (pinned host copy) and the plan bank ------------------------------------------
-    t0 = time.perf_counter()
-    bp = pool.draw_batch(lengths, workload.SAMPLE_RATE, args, algo, seeds)
-    t_plan = time.perf_counter() - t0
+    planners = []
+    if native:
+        from scl_deepfake_audio_detection_b200.native_planner import NativePlanner
+        planners = [NativePlanner(threads=workers, pinned=True) for _ in range(3)]  # [0]: resident bank, [1],[2]: e2e double buffer
+        t0 = time.perf_counter()
+        bp = planners[0].draw(lengths, workload.SAMPLE_RATE, args, algo, seeds=seeds)
+        t_plan = time.perf_counter() - t0
+        # guard: the native planner must reproduce the numpy draws (integers and float32 taps) on a sample
+        ref = pool.draw_batch(lengths[:4], workload.SAMPLE_RATE, args, algo, seeds[:4], ld=bp.ld)
+        for name in ("lnl_tap_off", "lnl_taps", "isd_off", "isd_idx", "isd_fr"):
+            r = getattr(ref, name)
+            if r is not None:
+                assert np.array_equal(r, getattr(bp, name)[:r.shape[0]]), f"native planner diverges from numpy on {name}"
+    else:
+        t0 = time.perf_counter()
+        bp = pool.draw_batch(lengths, workload.SAMPLE_RATE, args, algo, seeds)
+        t_plan = time.perf_counter() - t0
     ld = bp.ld
     x_host = torch.empty((B, ld), dtype=torch.float32).pin_memory()
     workload.synth_batch(lo, B, L, ld, out=x_host.numpy())
@@ -275,7 +290,37 @@ def gpu_arm(a):
     value = world * B / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C ABI: plan draw (host, parallel) + H2D + kernels + D2H every step ---
+    def e2e_run_native(steps, warm):
+        """Plan drawing for step i+1 runs on the planner's host threads (no GIL) while step i is on the GPU."""
+        import threading
+        slots = planners[1:]
+        box = {}
+
+        def draw_into(k):
+            box[k] = slots[k % 2].draw(lengths, workload.SAMPLE_RATE, args, algo, seeds=seeds, ld=ld)
+
+        def run_steps(n):
+            th = threading.Thread(target=draw_into, args=(0,))
+            th.start()
+            for k in range(n):
+                th.join()
+                plan_k = box.pop(k)
+                if k + 1 < n:
+                    th = threading.Thread(target=draw_into, args=(k + 1,))
+                    th.start()
+                eng.process_host(algo, x_host.numpy(), plan_k, out=y_host.numpy())
+
+        run_steps(warm)
+        sharding.barrier()
+        t0 = time.perf_counter()
+        run_steps(steps)
+        dt = time.perf_counter() - t0
+        sharding.barrier()
+        return dt / steps
+
     def e2e_run(steps, warm):
+        if native:
+            return e2e_run_native(steps, warm)
         pending = pool.pool.map_async(workload._draw_chunk, _plan_jobs(lengths, args, algo, seeds, workers)) if pool.pool else None
 
         def next_plan():
@@ -334,7 +379,7 @@ def gpu_arm(a):
             "config": {"workload": workload_name(algo, B, L), "algo": algo, "batch_per_gpu": B, "global_batch": world * B, "utt_len": L,
                        "sharding": f"utterances by index over {world} GPU(s), no collective",
                        "l2": "inputs (%.2f GB per GPU) larger than L2; no explicit flush" % (x.numel() * 4 / 1e9),
-                       "plan_bank": "drawn on the host with the reference's numpy calls, resident in HBM before timing",
+                       "plan_bank": "drawn on the host (%s planner, reference RNG stream order), resident in HBM before timing" % a.planner,
                        "step_ms_min_max": [min(step_ms), max(step_ms)], "plan_draw_s_setup": t_plan, "host_plan_workers": workers},
             "roofline": {
                 "bound": "fp32", "kernel": "fir_bank_kernel", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -348,7 +393,10 @@ def gpu_arm(a):
                              "algorithmic_bytes_per_step": bytes_step},
             },
             "e2e": {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "includes": "host plan draw (numpy/scipy, %d worker processes, overlapped with the previous step) + H2D + kernels + D2H" % workers,
+                    "includes": ("host plan draw (%s, %d host %s, overlapped with the previous step) + H2D + kernels + D2H"
+                                 % (("native planner: bit-exact numpy MT19937 stream + float64 filter design", workers, "threads") if native
+                                    else ("numpy/scipy", workers, "processes"))),
+                    "plan_draw_s_per_batch": t_plan,
                     "ms_per_step": e2e_s * 1e3, "copy_and_kernels_only_ms_per_step": copy_s * 1e3,
                     "copy_and_kernels_only_value": world * B / copy_s, "steps": e2e_steps, "result_check_max_abs": check},
             "gpu_launches": launches,
@@ -378,6 +426,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="utterances per GPU per step (BASELINE config 3: 4096)")
     ap.add_argument("--length", type=int, default=64600)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--planner", choices=["native", "numpy"], default="native",
+                    help="host plan drawing: the native bit-exact re-implementation (default) or the numpy calls themselves")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--cpu-per-core", type=int, default=8, help="utterances per host core per CPU-baseline step")

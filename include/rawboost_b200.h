@@ -134,6 +134,35 @@ RB_API int rb_process_host(rb_ctx* ctx, int algo, const float* x, const int32_t*
 /* bytes moved by the last rb_process_host call: host->device and device->host */
 RB_API int rb_ctx_last_traffic(const rb_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
+/* ---- native host-side plan drawing (optional accelerator for the numpy path in plans.py) -------------------------
+ * Bit-exact re-implementation of the numpy legacy MT19937 calls the reference makes (RawBoost.py:15,79,80,90: uniform,
+ * permutation, rand, normal; seeding as np.random.seed(int)) plus the float64 filter design of genNotchCoeffs
+ * (RawBoost.py:28-48). Integer results and the stream state are identical to numpy's; tap values agree to ~1e-15.
+ * rb_args carries the reference's knobs (main.py:258-298) and the sample rate. */
+typedef struct rb_args {
+  int32_t N_f, nBands;
+  double minF, maxF, minBW, maxBW, minCoeff, maxCoeff, minG, maxG, minBiasLinNonLin, maxBiasLinNonLin;
+  double P, g_sd, SNRmin, SNRmax, fs;
+} rb_args;
+/* numpy's RandomState.get_state() in C: ('MT19937', key[624], pos, has_gauss, cached_gaussian) */
+typedef struct rb_rng_state {
+  uint32_t key[624];
+  int32_t pos;
+  int32_t has_gauss;
+  double cached_gaussian;
+} rb_rng_state;
+typedef struct rb_planner rb_planner;
+/* threads <= 0: one per hardware thread. pinned != 0: plan buffers are page-locked (needs a CUDA device). */
+RB_API int rb_planner_create(rb_planner** out, int threads, int pinned);
+RB_API int rb_planner_destroy(rb_planner* planner);
+/* Draw the plans process_Rawboost_feature(., ., args, algo) would draw for B utterances of len[u] samples.
+ * seeds != NULL: np.random.seed(seeds[u]) precedes utterance u (independent, drawn in parallel by the thread pool).
+ * seeds == NULL: the utterances consume ONE stream, *state, one after another, and *state is advanced.
+ * *view receives HOST pointers (rb_plan layout, ssi_noise rows of stride ld) valid until the next draw on this planner;
+ * pass it to rb_process_host. */
+RB_API int rb_planner_draw(rb_planner* planner, const rb_args* args, int algo, int B, int ld, const int32_t* len,
+                           const uint32_t* seeds, rb_rng_state* state, rb_plan* view);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------------------
  * rb_probe_fp32: runs a register-resident FFMA2 (packed=1) or FFMA (packed=0) chain on every SM and
  * returns the achieved FLOP count in *flops; the caller times it with events on `stream`.

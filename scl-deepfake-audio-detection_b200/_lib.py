@@ -17,7 +17,8 @@ RB_ABI_VERSION = 1
 SYMBOLS = (
     "rb_error_string", "rb_abi_version", "rb_workspace_bytes", "rb_filter_fir", "rb_normwav", "rb_lnl", "rb_isd",
     "rb_ssi", "rb_process", "rb_ctx_create", "rb_ctx_destroy", "rb_process_host", "rb_ctx_last_traffic",
-    "rb_probe_fp32", "rb_launch_count", "rb_profile_enable", "rb_profile_read",
+    "rb_probe_fp32", "rb_launch_count", "rb_profile_enable", "rb_profile_read", "rb_planner_create", "rb_planner_destroy",
+    "rb_planner_draw",
 )
 
 
@@ -40,6 +41,18 @@ class RbPlan(C.Structure):
         ("ssi_tap_off", C.c_void_p),
         ("ssi_snr_db", C.c_void_p),
     ]
+
+
+class RbArgs(C.Structure):
+    """``struct rb_args``: the reference's RawBoost knobs (main.py:258-298) plus the sample rate."""
+    _fields_ = [("N_f", C.c_int32), ("nBands", C.c_int32)] + [(n, C.c_double) for n in (
+        "minF", "maxF", "minBW", "maxBW", "minCoeff", "maxCoeff", "minG", "maxG", "minBiasLinNonLin", "maxBiasLinNonLin",
+        "P", "g_sd", "SNRmin", "SNRmax", "fs")]
+
+
+class RbRngState(C.Structure):
+    """``struct rb_rng_state``: numpy's legacy MT19937 state."""
+    _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int32), ("has_gauss", C.c_int32), ("cached_gaussian", C.c_double)]
 
 
 _lib = None
@@ -94,6 +107,12 @@ def load() -> C.CDLL:
     lib.rb_profile_enable.argtypes = [i32]
     lib.rb_profile_read.restype = i32
     lib.rb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), i32]
+    lib.rb_planner_create.restype = i32
+    lib.rb_planner_create.argtypes = [C.POINTER(vp), i32, i32]
+    lib.rb_planner_destroy.restype = i32
+    lib.rb_planner_destroy.argtypes = [vp]
+    lib.rb_planner_draw.restype = i32
+    lib.rb_planner_draw.argtypes = [vp, C.POINTER(RbArgs), i32, i32, i32, vp, vp, C.POINTER(RbRngState), C.POINTER(RbPlan)]
     if lib.rb_abi_version() != RB_ABI_VERSION:
         raise RawBoostLibraryError(f"ABI mismatch: library {lib.rb_abi_version()}, binding {RB_ABI_VERSION}; rebuild")
     _lib = lib

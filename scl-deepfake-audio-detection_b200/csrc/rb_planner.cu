@@ -1,0 +1,517 @@
+// rb_planner.cu -- native host-side plan drawing (host code only; no kernels).
+//
+// The reference draws every random parameter of RawBoost from numpy's process-global legacy MT19937 stream
+// (/root/reference/datautils/RawBoost.py:15,79,80,90). The Python path in plans.py issues those numpy calls itself and
+// is the contract; this file is the fast equivalent for batched use: a bit-exact re-implementation of the pieces of
+// numpy's legacy generator the path consumes --
+//   seeding          np.random.seed(int)            -> mt19937_seed (Knuth LCG fill)
+//   uniform          low + (high-low) * double53    -> two 32-bit words per double, (a>>5, b>>6)
+//   permutation(n)   arange + legacy shuffle        -> Fisher-Yates from the end, masked rejection on 32-bit words
+//   rand(n)          double53
+//   normal(0,1,n)    legacy polar Box-Muller with the cached second value
+// -- plus the float64 filter design of genNotchCoeffs (RawBoost.py:28-48: Hamming-windowed two-band firwin stages,
+// cascade convolution, peak normalisation on the 512-point freqz grid). Integer results (tap counts, impulse count and
+// positions) and the stream state are bit-identical to numpy's; tap values agree to ~1e-15 relative (libm vs numpy's SIMD
+// sin/cos, radix-2 FFT vs pocketfft), far inside the float32 they are shipped as. tests/test_host_logic.py checks both.
+//
+// Utterances are drawn by a pool of host threads straight into page-locked CSR buffers laid out as struct rb_plan.
+#include <math.h>
+#include <string.h>
+#include <atomic>
+#include <complex>
+#include <thread>
+#include <vector>
+
+#include "rb_common.cuh"
+
+namespace {
+
+constexpr int kMT = 624;
+
+struct Mt {
+  uint32_t key[kMT];   // raw state, numpy layout
+  uint32_t out[kMT];   // tempered outputs of the current block (filled by regen, consumed by u32)
+  int pos;
+  int has_gauss;
+  double gauss;
+
+  void seed(uint32_t s) {
+    for (int i = 0; i < kMT; ++i) {
+      key[i] = s;
+      s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+    }
+    pos = kMT;
+    has_gauss = 0;
+    gauss = 0.0;
+  }
+  // Adopt a numpy state whose block is partly consumed: temper the current block so u32() can continue at `pos`.
+  void adopt(const uint32_t* k, int p, int hg, double g) {
+    memcpy(key, k, sizeof(key));
+    pos = p;
+    has_gauss = hg;
+    gauss = g;
+    temper_block();
+  }
+  void temper_block() {
+    for (int i = 0; i < kMT; ++i) {
+      uint32_t y = key[i];
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= (y >> 18);
+      out[i] = y;
+    }
+  }
+  void regen() {
+    constexpr uint32_t kUpper = 0x80000000u, kLower = 0x7fffffffu, kMatrix = 0x9908b0dfu;
+    constexpr int N = kMT, M = 397;
+    int i;
+    for (i = 0; i < N - M; ++i) {
+      const uint32_t y = (key[i] & kUpper) | (key[i + 1] & kLower);
+      key[i] = key[i + M] ^ (y >> 1) ^ (-(int32_t)(y & 1) & kMatrix);
+    }
+    for (; i < N - 1; ++i) {
+      const uint32_t y = (key[i] & kUpper) | (key[i + 1] & kLower);
+      key[i] = key[i + (M - N)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & kMatrix);
+    }
+    const uint32_t y = (key[N - 1] & kUpper) | (key[0] & kLower);
+    key[N - 1] = key[M - 1] ^ (y >> 1) ^ (-(int32_t)(y & 1) & kMatrix);
+    temper_block();
+    pos = 0;
+  }
+  inline uint32_t u32() {
+    if (__builtin_expect(pos == kMT, 0)) regen();
+    return out[pos++];
+  }
+  inline double dbl() {
+    const int32_t a = (int32_t)(u32() >> 5), b = (int32_t)(u32() >> 6);
+    return (a * 67108864.0 + b) / 9007199254740992.0;
+  }
+  inline double uniform(double lo, double hi) { return lo + (hi - lo) * dbl(); }
+  inline uint32_t interval(uint32_t max) {  // numpy random_interval, max <= 0xffffffff
+    if (max == 0) return 0;
+    uint32_t mask = max;
+    mask |= mask >> 1;
+    mask |= mask >> 2;
+    mask |= mask >> 4;
+    mask |= mask >> 8;
+    mask |= mask >> 16;
+    uint32_t v;
+    while ((v = (u32() & mask)) > max) {
+    }
+    return v;
+  }
+  double gauss_legacy() {
+    if (has_gauss) {
+      const double t = gauss;
+      has_gauss = 0;
+      gauss = 0.0;
+      return t;
+    }
+    double f, x1, x2, r2;
+    do {
+      x1 = 2.0 * dbl() - 1.0;
+      x2 = 2.0 * dbl() - 1.0;
+      r2 = x1 * x1 + x2 * x2;
+    } while (r2 >= 1.0 || r2 == 0.0);
+    f = sqrt(-2.0 * log(r2) / r2);
+    gauss = f * x1;
+    has_gauss = 1;
+    return f * x2;
+  }
+};
+
+// ---- filter design ------------------------------------------------------------------------------------------------
+void fft1024(std::complex<double>* a) {  // in-place radix-2 DIT, n = 1024
+  constexpr int n = 1024;
+  static std::complex<double> tw[n / 2];
+  static std::atomic<int> ready{0};
+  static std::atomic<int> lock{0};
+  if (!ready.load(std::memory_order_acquire)) {
+    int expected = 0;
+    if (lock.compare_exchange_strong(expected, 1)) {
+      for (int k = 0; k < n / 2; ++k) tw[k] = std::complex<double>(cos(-2.0 * M_PI * k / n), sin(-2.0 * M_PI * k / n));
+      ready.store(1, std::memory_order_release);
+    } else {
+      while (!ready.load(std::memory_order_acquire)) {
+      }
+    }
+  }
+  for (int i = 1, j = 0; i < n; ++i) {
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(a[i], a[j]);
+  }
+  for (int len = 2; len <= n; len <<= 1) {
+    const int step = n / len;
+    for (int i = 0; i < n; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * tw[k * step];
+        a[i + k] = u + v;
+        a[i + k + len / 2] = u - v;
+      }
+  }
+}
+
+// max |H(w)| on scipy.signal.freqz's default grid (512 points on [0, pi)); FFT path for K <= 1024, direct otherwise.
+double peak_response(const std::vector<double>& b) {
+  const int K = (int)b.size();
+  double best = 0.0;
+  if (K <= 1024) {
+    std::complex<double> buf[1024];
+    for (int i = 0; i < 1024; ++i) buf[i] = std::complex<double>(i < K ? b[i] : 0.0, 0.0);
+    fft1024(buf);
+    for (int i = 0; i < 512; ++i) best = fmax(best, std::abs(buf[i]));
+  } else {
+    for (int i = 0; i < 512; ++i) {
+      const double w = M_PI * i / 512.0;
+      double re = 0.0, im = 0.0;
+      for (int k = 0; k < K; ++k) {
+        re += b[k] * cos(w * k);
+        im -= b[k] * sin(w * k);
+      }
+      best = fmax(best, hypot(re, im));
+    }
+  }
+  return best;
+}
+
+inline double sinc_pi(double x) {  // numpy.sinc
+  if (x == 0.0) return 1.0;
+  const double y = M_PI * x;
+  return sin(y) / y;
+}
+
+// scipy.signal.firwin(n, [f1, f2], window='hamming', fs=fs) with the default pass_zero=True: a band-stop, DC gain 1.
+void firwin_bandstop(int n, double f1, double f2, double fs, std::vector<double>& h) {
+  const double nyq = fs / 2.0, c1 = f1 / nyq, c2 = f2 / nyq, alpha = 0.5 * (n - 1);
+  h.resize(n);
+  double dc = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double m = i - alpha;
+    // bands [0, c1] and [c2, 1]
+    double v = c1 * sinc_pi(c1 * m);  // same association as scipy's loop over the bands
+    v -= 0.0 * sinc_pi(0.0 * m);
+    v += 1.0 * sinc_pi(1.0 * m);
+    v -= c2 * sinc_pi(c2 * m);
+    const double win = (n == 1) ? 1.0 : 0.54 - 0.46 * cos(2.0 * M_PI * i / (n - 1));
+    h[i] = v * win;
+    dc += h[i];  // scale_frequency = 0 -> cos term is 1
+  }
+  for (int i = 0; i < n; ++i) h[i] /= dc;
+}
+
+struct Args {  // mirrors rb_args
+  int32_t N_f, nBands;
+  double minF, maxF, minBW, maxBW, minCoeff, maxCoeff, minG, maxG, minBiasLinNonLin, maxBiasLinNonLin, P, g_sd, SNRmin, SNRmax, fs;
+};
+
+// genNotchCoeffs (RawBoost.py:28-48): 3*nBands + 1 uniforms.
+void gen_notch(Mt& rng, const Args& a, double minG, double maxG, std::vector<double>& taps, std::vector<double>& stage,
+               std::vector<double>& tmp) {
+  taps.assign(1, 1.0);
+  for (int band = 0; band < a.nBands; ++band) {
+    const double fc = rng.uniform(a.minF, a.maxF);
+    const double bw = rng.uniform(a.minBW, a.maxBW);
+    int c = (int)rng.uniform(a.minCoeff, a.maxCoeff);  // int() truncation
+    if (c % 2 == 0) c += 1;
+    double f1 = fc - bw / 2, f2 = fc + bw / 2;
+    if (f1 <= 0) f1 = 1.0 / 1000;
+    if (f2 >= a.fs / 2) f2 = a.fs / 2 - 1.0 / 1000;
+    firwin_bandstop(c, f1, f2, a.fs, stage);
+    tmp.assign(taps.size() + stage.size() - 1, 0.0);
+    for (size_t i = 0; i < stage.size(); ++i)
+      for (size_t j = 0; j < taps.size(); ++j) tmp[i + j] += stage[i] * taps[j];
+    taps.swap(tmp);
+  }
+  const double G = rng.uniform(minG, maxG);
+  const double scale = pow(10.0, G / 20.0) / peak_response(taps);
+  for (double& t : taps) t *= scale;
+}
+
+struct UttDraw {
+  std::vector<float> lnl_taps;
+  std::vector<int32_t> lnl_k;
+  std::vector<int32_t> isd_idx;
+  std::vector<double> isd_fr;
+  std::vector<float> ssi_taps;
+  float snr = 0.f;
+};
+
+struct Scratch {
+  std::vector<double> taps, stage, tmp;
+  std::vector<uint32_t> perm;
+  std::vector<uint16_t> perm16;
+};
+
+// numpy's legacy shuffle of arange(n): for i = n-1 .. 1: j = random_interval(i); swap(x[i], x[j]). The mask only changes
+// when i crosses a power of two, so it is hoisted out of the inner loop.
+template <typename T>
+void shuffle_legacy(Mt& rng, T* x, int n) {
+  int i = n - 1;
+  while (i >= 1) {
+    uint32_t mask = (uint32_t)i;
+    mask |= mask >> 1;
+    mask |= mask >> 2;
+    mask |= mask >> 4;
+    mask |= mask >> 8;
+    mask |= mask >> 16;
+    const int lo = (int)(mask >> 1) + 1;  // smallest i with this mask
+    for (; i >= lo && i >= 1; --i) {
+      uint32_t j;
+      while ((j = (rng.u32() & mask)) > (uint32_t)i) {
+      }
+      const T t = x[j];
+      x[j] = x[i];
+      x[i] = t;
+    }
+  }
+}
+
+// All draws of process_Rawboost_feature for one utterance, in the dispatcher's order: LnL, ISD, SSI.
+void draw_utt(Mt& rng, const Args& a, int algo, int length, UttDraw& out, float* noise_row, Scratch& sc) {
+  const bool lnl = (algo == 1 || algo == 4 || algo == 5 || algo == 6 || algo == 8);
+  const bool isd = (algo == 2 || algo == 4 || algo == 5 || algo == 7 || algo == 8);
+  const bool ssi = (algo == 3 || algo == 4 || algo == 6 || algo == 7);
+  out.lnl_taps.clear();
+  out.lnl_k.clear();
+  out.isd_idx.clear();
+  out.isd_fr.clear();
+  out.ssi_taps.clear();
+  if (lnl) {
+    double minG = a.minG, maxG = a.maxG;
+    for (int f = 0; f < a.N_f; ++f) {
+      if (f == 1) {
+        minG -= a.minBiasLinNonLin;
+        maxG -= a.maxBiasLinNonLin;
+      }
+      gen_notch(rng, a, minG, maxG, sc.taps, sc.stage, sc.tmp);
+      out.lnl_k.push_back((int32_t)sc.taps.size());
+      for (double t : sc.taps) out.lnl_taps.push_back((float)t);
+    }
+  }
+  if (isd) {
+    const double beta = rng.uniform(0.0, a.P);
+    const int n = (int)(length * (beta / 100));
+    out.isd_idx.resize(n);
+    out.isd_fr.resize(n);
+    if (length <= 65536) {  // 16-bit permutation array: half the cache footprint of the Fisher-Yates walk
+      sc.perm16.resize(length);
+      uint16_t* pm = sc.perm16.data();
+      for (int i = 0; i < length; ++i) pm[i] = (uint16_t)i;
+      shuffle_legacy(rng, pm, length);
+      for (int i = 0; i < n; ++i) out.isd_idx[i] = (int32_t)pm[i];
+    } else {
+      sc.perm.resize(length);
+      uint32_t* pm = sc.perm.data();
+      for (int i = 0; i < length; ++i) pm[i] = (uint32_t)i;
+      shuffle_legacy(rng, pm, length);
+      for (int i = 0; i < n; ++i) out.isd_idx[i] = (int32_t)pm[i];
+    }
+    for (int i = 0; i < n; ++i) out.isd_fr[i] = 2 * rng.dbl() - 1;
+    for (int i = 0; i < n; ++i) out.isd_fr[i] *= 2 * rng.dbl() - 1;
+  }
+  if (ssi) {
+    for (int i = 0; i < length; ++i) noise_row[i] = (float)(0.0 + 1.0 * rng.gauss_legacy());
+    gen_notch(rng, a, a.minG, a.maxG, sc.taps, sc.stage, sc.tmp);
+    for (double t : sc.taps) out.ssi_taps.push_back((float)t);
+    out.snr = (float)rng.uniform(a.SNRmin, a.SNRmax);
+  }
+}
+
+template <typename T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  bool pinned = false;
+  int ensure(size_t n, bool want_pinned) {
+    if (n <= cap) return 0;
+    release();
+    const size_t bytes = (n + n / 8 + 64) * sizeof(T);
+    if (want_pinned && cudaMallocHost((void**)&p, bytes) == cudaSuccess) {
+      pinned = true;
+    } else {
+      (void)cudaGetLastError();
+      p = (T*)malloc(bytes);
+      pinned = false;
+      if (!p) return -1;
+    }
+    cap = bytes / sizeof(T);
+    return 0;
+  }
+  void release() {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p);
+    else free(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct rb_planner {
+  int threads;
+  bool pinned;
+  std::vector<UttDraw> draws;
+  PinnedBuf<float> lnl_taps, ssi_taps, ssi_noise, ssi_snr;
+  PinnedBuf<int32_t> lnl_off, isd_off, isd_idx, ssi_off;
+  PinnedBuf<double> isd_fr;
+};
+
+extern "C" {
+
+int rb_planner_create(rb_planner** out, int threads, int pinned) {
+  if (!out) return RB_ERR_INVALID_ARG;
+  rb_planner* p = new (std::nothrow) rb_planner();
+  if (!p) return RB_ERR_INVALID_ARG;
+  p->threads = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  p->pinned = pinned != 0;
+  *out = p;
+  return RB_OK;
+}
+
+int rb_planner_destroy(rb_planner* p) {
+  if (!p) return RB_OK;
+  p->lnl_taps.release();
+  p->ssi_taps.release();
+  p->ssi_noise.release();
+  p->ssi_snr.release();
+  p->lnl_off.release();
+  p->isd_off.release();
+  p->isd_idx.release();
+  p->ssi_off.release();
+  p->isd_fr.release();
+  delete p;
+  return RB_OK;
+}
+
+// Draw the plans of B utterances. seeds != NULL: np.random.seed(seeds[u]) before utterance u (utterances independent,
+// drawn in parallel). seeds == NULL: the utterances consume ONE stream, `state` (numpy get_state layout), sequentially,
+// and `state` is advanced -- what a loader calling the reference once per view does. `view` receives host pointers into
+// the planner's buffers, valid until the next draw on this planner.
+int rb_planner_draw(rb_planner* p, const rb_args* args, int algo, int B, int ld, const int32_t* len, const uint32_t* seeds,
+                    rb_rng_state* state, rb_plan* view) {
+  if (!p || !args || !view || B < 0 || ld < 0 || (B > 0 && !len)) return RB_ERR_INVALID_ARG;
+  if (!seeds && !state) return RB_ERR_INVALID_ARG;
+  Args a;
+  a.N_f = args->N_f;
+  a.nBands = args->nBands;
+  a.minF = args->minF;
+  a.maxF = args->maxF;
+  a.minBW = args->minBW;
+  a.maxBW = args->maxBW;
+  a.minCoeff = args->minCoeff;
+  a.maxCoeff = args->maxCoeff;
+  a.minG = args->minG;
+  a.maxG = args->maxG;
+  a.minBiasLinNonLin = args->minBiasLinNonLin;
+  a.maxBiasLinNonLin = args->maxBiasLinNonLin;
+  a.P = args->P;
+  a.g_sd = args->g_sd;
+  a.SNRmin = args->SNRmin;
+  a.SNRmax = args->SNRmax;
+  a.fs = args->fs;
+  const bool lnl = (algo == 1 || algo == 4 || algo == 5 || algo == 6 || algo == 8);
+  const bool isd = (algo == 2 || algo == 4 || algo == 5 || algo == 7 || algo == 8);
+  const bool ssi = (algo == 3 || algo == 4 || algo == 6 || algo == 7);
+  memset(view, 0, sizeof(*view));
+  view->n_f = lnl ? a.N_f : 0;
+  view->g_sd = (float)a.g_sd;
+  if (B == 0) return RB_OK;
+  for (int u = 0; u < B; ++u)
+    if (len[u] < 0 || len[u] > ld) return RB_ERR_INVALID_ARG;
+  p->draws.resize(B);
+  if (ssi) {
+    if (p->ssi_noise.ensure((size_t)B * ld, p->pinned)) return RB_ERR_INVALID_ARG;
+    memset(p->ssi_noise.p, 0, (size_t)B * ld * sizeof(float));
+  }
+  if (seeds) {
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      Mt rng;
+      Scratch sc;
+      for (;;) {
+        const int u = next.fetch_add(1);
+        if (u >= B) break;
+        rng.seed(seeds[u]);
+        draw_utt(rng, a, algo, len[u], p->draws[u], ssi ? p->ssi_noise.p + (size_t)u * ld : nullptr, sc);
+      }
+    };
+    const int nt = std::max(1, std::min(p->threads, B));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  } else {
+    Mt rng;
+    rng.adopt(state->key, state->pos, state->has_gauss, state->cached_gaussian);
+    Scratch sc;
+    for (int u = 0; u < B; ++u) draw_utt(rng, a, algo, len[u], p->draws[u], ssi ? p->ssi_noise.p + (size_t)u * ld : nullptr, sc);
+    memcpy(state->key, rng.key, sizeof(rng.key));
+    state->pos = rng.pos;
+    state->has_gauss = rng.has_gauss;
+    state->cached_gaussian = rng.gauss;
+  }
+  // ---- pack into CSR ------------------------------------------------------------------------------------------------
+  if (lnl) {
+    size_t total = 0;
+    for (int u = 0; u < B; ++u) total += p->draws[u].lnl_taps.size();
+    if (p->lnl_taps.ensure(total, p->pinned) || p->lnl_off.ensure((size_t)B * a.N_f + 1, p->pinned)) return RB_ERR_INVALID_ARG;
+    size_t off = 0;
+    p->lnl_off.p[0] = 0;
+    for (int u = 0; u < B; ++u) {
+      const UttDraw& d = p->draws[u];
+      memcpy(p->lnl_taps.p + off, d.lnl_taps.data(), d.lnl_taps.size() * sizeof(float));
+      size_t o = off;
+      for (int f = 0; f < a.N_f; ++f) {
+        o += d.lnl_k[f];
+        p->lnl_off.p[(size_t)u * a.N_f + f + 1] = (int32_t)o;
+      }
+      off = o;
+    }
+    view->lnl_taps = p->lnl_taps.p;
+    view->lnl_tap_off = p->lnl_off.p;
+  }
+  if (isd) {
+    size_t total = 0;
+    for (int u = 0; u < B; ++u) total += p->draws[u].isd_idx.size();
+    if (p->isd_idx.ensure(total, p->pinned) || p->isd_fr.ensure(total, p->pinned) || p->isd_off.ensure((size_t)B + 1, p->pinned))
+      return RB_ERR_INVALID_ARG;
+    size_t off = 0;
+    p->isd_off.p[0] = 0;
+    for (int u = 0; u < B; ++u) {
+      const UttDraw& d = p->draws[u];
+      memcpy(p->isd_idx.p + off, d.isd_idx.data(), d.isd_idx.size() * sizeof(int32_t));
+      memcpy(p->isd_fr.p + off, d.isd_fr.data(), d.isd_fr.size() * sizeof(double));
+      off += d.isd_idx.size();
+      p->isd_off.p[u + 1] = (int32_t)off;
+    }
+    view->isd_off = p->isd_off.p;
+    view->isd_idx = p->isd_idx.p;
+    view->isd_fr = p->isd_fr.p;
+  }
+  if (ssi) {
+    size_t total = 0;
+    for (int u = 0; u < B; ++u) total += p->draws[u].ssi_taps.size();
+    if (p->ssi_taps.ensure(total, p->pinned) || p->ssi_off.ensure((size_t)B + 1, p->pinned) || p->ssi_snr.ensure((size_t)B, p->pinned))
+      return RB_ERR_INVALID_ARG;
+    size_t off = 0;
+    p->ssi_off.p[0] = 0;
+    for (int u = 0; u < B; ++u) {
+      const UttDraw& d = p->draws[u];
+      memcpy(p->ssi_taps.p + off, d.ssi_taps.data(), d.ssi_taps.size() * sizeof(float));
+      off += d.ssi_taps.size();
+      p->ssi_off.p[u + 1] = (int32_t)off;
+      p->ssi_snr.p[u] = d.snr;
+    }
+    view->ssi_noise = p->ssi_noise.p;
+    view->ssi_taps = p->ssi_taps.p;
+    view->ssi_tap_off = p->ssi_off.p;
+    view->ssi_snr_db = p->ssi_snr.p;
+  }
+  return RB_OK;
+}
+
+}  // extern "C"

@@ -206,3 +206,77 @@ def test_two_rank_gloo_sharding(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out.decode()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# native planner (csrc/rb_planner.cu): bit-exact with the numpy calls of plans.py
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def native():
+    from scl_deepfake_audio_detection_b200.native_planner import NativePlanner
+    return NativePlanner(threads=2, pinned=False)
+
+
+def _same_plan(a, b):
+    for name in ("lnl_tap_off", "isd_off", "isd_idx", "ssi_tap_off"):
+        x, y = getattr(a, name), getattr(b, name)
+        assert (x is None) == (y is None), name
+        if x is not None:
+            assert x.dtype == y.dtype and np.array_equal(x, y), name      # integer work: bit-exact
+    for name in ("isd_fr", "ssi_noise", "ssi_snr_db"):
+        x, y = getattr(a, name), getattr(b, name)
+        if y is not None:
+            assert np.array_equal(x, y), name                              # pure MT19937 arithmetic: bit-exact
+    for name in ("lnl_taps", "ssi_taps"):
+        x, y = getattr(a, name), getattr(b, name)
+        if y is not None:                                                  # libm vs numpy SIMD: <= 1 float32 ulp
+            np.testing.assert_allclose(x, y, rtol=1.3e-7, atol=1e-12, err_msg=name)
+    assert a.n_f == b.n_f and a.g_sd == b.g_sd and a.ld == b.ld
+
+
+@pytest.mark.parametrize("algo", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_native_planner_matches_numpy_per_utterance_seeds(P, native, algo):
+    lens = [64600, 1, 2, 37, 4097, 70001, 16000]
+    seeds = [orc.seed_for(u) for u in range(len(lens))]
+    a = native.draw(lens, 16000, ARGS, algo, seeds=seeds, copy=True)
+    b = P.draw_batch(lens, 16000, ARGS, algo, seeds=seeds)
+    _same_plan(a, b)
+
+
+def test_native_planner_continues_the_global_numpy_stream(P, native, golden):
+    """Stream mode: consumes np.random's global state exactly as the reference's calls do (digests from the reference)."""
+    _, meta = golden
+    for algo in (2, 4, 5):
+        for u in (0, 1):
+            c = meta["cases"][f"algo{algo}_loud0_u{u}"]
+            np.random.seed(orc.seed_for(u))
+            native.draw([c["L"]], 16000, ARGS, algo, use_global_stream=True)
+            assert stream_digest() == c["stream"]
+    # mid-block start and a cached gaussian carried in and out
+    np.random.seed(5)
+    np.random.normal(size=3)
+    b = P.draw_batch([3001, 64600], 16000, ARGS, 7)
+    ref_state = np.random.get_state()
+    np.random.seed(5)
+    np.random.normal(size=3)
+    a = native.draw([3001, 64600], 16000, ARGS, 7, use_global_stream=True, copy=True)
+    got = np.random.get_state()
+    _same_plan(a, b)
+    assert np.array_equal(ref_state[1], got[1]) and ref_state[2:] == got[2:]
+
+
+def test_native_planner_nondefault_args(P, native):
+    args = orc.make_args(nBands=7, maxCoeff=300, minCoeff=3, N_f=3, P=37, g_sd=5, SNRmin=0, SNRmax=3, minG=-4, maxG=6, minF=1, maxF=7999)
+    a = native.draw([20000, 333], 16000, args, 4, seeds=[9, 10], copy=True)
+    b = P.draw_batch([20000, 333], 16000, args, 4, seeds=[9, 10])
+    _same_plan(a, b)
+    assert np.diff(a.lnl_tap_off).max() > 512  # cascades longer than one staged segment
+
+
+def test_workload_matches_oracle_workload():
+    from scl_deepfake_audio_detection_b200 import workload
+    for u in (0, 1, 7):
+        for loud in (False, True):
+            assert np.array_equal(workload.synth_utterance(u, 5000, loud), orc.synth_utterance(u, 5000, loud))
+        assert workload.seed_for(u) == orc.seed_for(u)
+    assert vars(workload.default_args()) == vars(orc.make_args())
