@@ -11,10 +11,14 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
        -Xptxas -v -I"$root/include" -I"$here" ${RB_EXTRA_FLAGS:-})
 objs=()
-for src in rb_fir_bank rb_dense rb_api rb_probe rb_planner; do
+for src in rb_fir_bank rb_dense rb_api rb_probe; do
   "$NVCC" "${FLAGS[@]}" -c "$here/$src.cu" -o "$out/$name.$src.o" 2> "$out/$name.$src.ptxas.log" || { cat "$out/$name.$src.ptxas.log" >&2; exit 1; }
   objs+=("$out/$name.$src.o")
 done
+# host-only planner: plain g++ (function multiversioning for the MT19937 block)
+CUDA_INC="$(dirname "$(dirname "$NVCC")")/include"
+"${CXX:-g++}" -O3 -std=c++17 -fPIC -fvisibility=hidden -I"$root/include" -I"$CUDA_INC" -c "$here/rb_planner.cpp" -o "$out/$name.rb_planner.o"
+objs+=("$out/$name.rb_planner.o")
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/$name.so" "${objs[@]}" -Xcompiler -fPIC
 grep -h -E "Used [0-9]+ registers|spill" "$out"/$name.*.ptxas.log | sort | uniq -c | sort -rn | head -20
 echo "built $out/$name.so"

@@ -1,4 +1,4 @@
-// rb_planner.cu -- native host-side plan drawing (host code only; no kernels).
+// rb_planner.cpp -- native host-side plan drawing (host code only, compiled by g++; no kernels).
 //
 // The reference draws every random parameter of RawBoost from numpy's process-global legacy MT19937 stream
 // (/root/reference/datautils/RawBoost.py:15,79,80,90). The Python path in plans.py issues those numpy calls itself and
@@ -22,11 +22,41 @@
 #include <thread>
 #include <vector>
 
-#include "rb_common.cuh"
+#include <cuda_runtime.h>  // cudaMallocHost for the page-locked plan buffers only
+#include "rawboost_b200.h"
 
 namespace {
 
 constexpr int kMT = 624;
+
+// One MT19937 block: advance the 624-word state in place and temper it into `out`. Compiled for AVX-512 / AVX2 / SSE2
+// and dispatched at load time (the build machine is not the machine it runs on).
+__attribute__((target_clones("avx512f", "avx2", "default")))
+void mt_block(uint32_t* __restrict__ key, uint32_t* __restrict__ out, int advance) {
+  constexpr uint32_t kUpper = 0x80000000u, kLower = 0x7fffffffu, kMatrix = 0x9908b0dfu;
+  constexpr int N = kMT, M = 397;
+  if (advance) {
+    int i;
+    for (i = 0; i < N - M; ++i) {
+      const uint32_t y = (key[i] & kUpper) | (key[i + 1] & kLower);
+      key[i] = key[i + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrix);
+    }
+    for (; i < N - 1; ++i) {
+      const uint32_t y = (key[i] & kUpper) | (key[i + 1] & kLower);
+      key[i] = key[i - (N - M)] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrix);
+    }
+    const uint32_t y = (key[N - 1] & kUpper) | (key[0] & kLower);
+    key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & kMatrix);
+  }
+  for (int i = 0; i < N; ++i) {
+    uint32_t y = key[i];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    out[i] = y;
+  }
+}
 
 struct Mt {
   uint32_t key[kMT];   // raw state, numpy layout
@@ -52,31 +82,9 @@ struct Mt {
     gauss = g;
     temper_block();
   }
-  void temper_block() {
-    for (int i = 0; i < kMT; ++i) {
-      uint32_t y = key[i];
-      y ^= (y >> 11);
-      y ^= (y << 7) & 0x9d2c5680u;
-      y ^= (y << 15) & 0xefc60000u;
-      y ^= (y >> 18);
-      out[i] = y;
-    }
-  }
+  void temper_block() { mt_block(key, out, 0); }
   void regen() {
-    constexpr uint32_t kUpper = 0x80000000u, kLower = 0x7fffffffu, kMatrix = 0x9908b0dfu;
-    constexpr int N = kMT, M = 397;
-    int i;
-    for (i = 0; i < N - M; ++i) {
-      const uint32_t y = (key[i] & kUpper) | (key[i + 1] & kLower);
-      key[i] = key[i + M] ^ (y >> 1) ^ (-(int32_t)(y & 1) & kMatrix);
-    }
-    for (; i < N - 1; ++i) {
-      const uint32_t y = (key[i] & kUpper) | (key[i + 1] & kLower);
-      key[i] = key[i + (M - N)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & kMatrix);
-    }
-    const uint32_t y = (key[N - 1] & kUpper) | (key[0] & kLower);
-    key[N - 1] = key[M - 1] ^ (y >> 1) ^ (-(int32_t)(y & 1) & kMatrix);
-    temper_block();
+    mt_block(key, out, 1);
     pos = 0;
   }
   inline uint32_t u32() {
