@@ -192,7 +192,7 @@ def gpu_arm(a):
     rank, local_rank, world = sharding.env_rank_world()
     cores = host_cores()
     workers = max(1, cores // max(1, world))
-    native = a.planner == "native"
+    native = a.planner in ("native", "device")  # the resident plan bank is drawn by the native host planner in both modes
     pool = workload.PlanPool(1 if native else workers)  # forked before CUDA is initialised; workers only run numpy/scipy
 
     import ctypes as C
@@ -318,7 +318,23 @@ def gpu_arm(a):
         sharding.barrier()
         return dt / steps
 
+    seeds_np = np.asarray(seeds, dtype=np.uint32)
+
+    def e2e_run_device(steps, warm):
+        """Seeds in, results out: plans are drawn on the device inside the pipelined host-buffer call."""
+        for _ in range(warm):
+            eng.process_host_seeded(algo, x_host.numpy(), bp.lengths, seeds_np, workload.SAMPLE_RATE, args, out=y_host.numpy())
+        sharding.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            eng.process_host_seeded(algo, x_host.numpy(), bp.lengths, seeds_np, workload.SAMPLE_RATE, args, out=y_host.numpy())
+        dt = time.perf_counter() - t0
+        sharding.barrier()
+        return dt / steps
+
     def e2e_run(steps, warm):
+        if a.planner == "device":
+            return e2e_run_device(steps, warm)
         if native:
             return e2e_run_native(steps, warm)
         pending = pool.pool.map_async(workload._draw_chunk, _plan_jobs(lengths, args, algo, seeds, workers)) if pool.pool else None
@@ -345,17 +361,22 @@ def gpu_arm(a):
         return dt / steps
 
     e2e_steps = max(1, min(a.steps, a.e2e_steps))
+    if a.host_chunk:
+        eng.set_host_chunk(a.host_chunk)
     if a.no_e2e:
         e2e_s, copy_s, h2d, d2h, check = float("nan"), float("nan"), 0, 0, None
     else:
-        e2e_s = sharding.max_over_ranks(e2e_run(e2e_steps, 1), dev)
+        e2e_s = sharding.max_over_ranks(e2e_run(e2e_steps, 2), dev)
         h2d, d2h = eng.last_host_traffic()
+        e2e_check = y_host.numpy()[:, :L].copy() if a.planner == "device" else None
         # copy + kernels only (plans pre-drawn), for the breakdown
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             eng.process_host(algo, x_host.numpy(), bp, out=y_host.numpy())
         copy_s = sharding.max_over_ranks((time.perf_counter() - t0) / e2e_steps, dev)
         check = float(np.abs(y_host.numpy()[:, :L]).max())
+        if e2e_check is not None:  # device-drawn plans must reproduce the host-drawn plan bank bit for bit
+            assert np.array_equal(e2e_check, y_host.numpy()[:, :L]), "device-planned e2e result differs from the host-planned one"
 
     # ---- CPU baseline on this box's host cores (N=1 only) -----------------------------------------------
     cpu = None
@@ -379,7 +400,7 @@ def gpu_arm(a):
             "config": {"workload": workload_name(algo, B, L), "algo": algo, "batch_per_gpu": B, "global_batch": world * B, "utt_len": L,
                        "sharding": f"utterances by index over {world} GPU(s), no collective",
                        "l2": "inputs (%.2f GB per GPU) larger than L2; no explicit flush" % (x.numel() * 4 / 1e9),
-                       "plan_bank": "drawn on the host (%s planner, reference RNG stream order), resident in HBM before timing" % a.planner,
+                       "plan_bank": "drawn on the host (%s planner, reference RNG stream order), resident in HBM before timing" % ("numpy" if a.planner == "numpy" else "native"),
                        "step_ms_min_max": [min(step_ms), max(step_ms)], "plan_draw_s_setup": t_plan, "host_plan_workers": workers},
             "roofline": {
                 "bound": "fp32", "kernel": "fir_bank_kernel", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -393,9 +414,13 @@ def gpu_arm(a):
                              "algorithmic_bytes_per_step": bytes_step},
             },
             "e2e": {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "includes": ("host plan draw (%s, %d host %s, overlapped with the previous step) + H2D + kernels + D2H"
-                                 % (("native planner: bit-exact numpy MT19937 stream + float64 filter design", workers, "threads") if native
-                                    else ("numpy/scipy", workers, "processes"))),
+                    "includes": ("H2D of waveforms + seeds, plan draw ON THE DEVICE (bit-exact replay of numpy's MT19937 stream, "
+                                 "rb_devplan_draw), kernels, D2H; chunked 3-stage pipeline through rb_process_host_seeded"
+                                 if a.planner == "device" else
+                                 "host plan draw (%s, %d host %s, overlapped with the previous step) + H2D + kernels + D2H"
+                                 % (("native planner: bit-exact numpy MT19937 stream + float64 filter design", workers, "threads")
+                                    if native else ("numpy/scipy", workers, "processes"))),
+                    "planner": a.planner,
                     "plan_draw_s_per_batch": t_plan,
                     "ms_per_step": e2e_s * 1e3, "copy_and_kernels_only_ms_per_step": copy_s * 1e3,
                     "copy_and_kernels_only_value": world * B / copy_s, "steps": e2e_steps, "result_check_max_abs": check},
@@ -426,8 +451,10 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="utterances per GPU per step (BASELINE config 3: 4096)")
     ap.add_argument("--length", type=int, default=64600)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--planner", choices=["native", "numpy"], default="native",
-                    help="host plan drawing: the native bit-exact re-implementation (default) or the numpy calls themselves")
+    ap.add_argument("--planner", choices=["device", "native", "numpy"], default="device",
+                    help="plan drawing in the e2e leg: on the device from per-utterance seeds (default), the native host "
+                         "re-implementation, or the numpy calls themselves")
+    ap.add_argument("--host-chunk", type=int, default=0, help="utterances per pipeline chunk of the host-buffer entry (0 = 4 per SM)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--cpu-per-core", type=int, default=8, help="utterances per host core per CPU-baseline step")

@@ -48,7 +48,8 @@ typedef enum rb_status {
   RB_ERR_ALIGNMENT = -2,     /* ld % 4 != 0 or a waveform pointer not 16-byte aligned     */
   RB_ERR_WORKSPACE = -3,     /* workspace smaller than rb_workspace_bytes()               */
   RB_ERR_NO_DEVICE = -4,     /* no CUDA device / wrong architecture (needs sm_100)        */
-  RB_ERR_PLAN = -5           /* a plan field required by the requested algo is missing    */
+  RB_ERR_PLAN = -5,          /* a plan field required by the requested algo is missing    */
+  RB_ERR_UNSUPPORTED = -6    /* arguments outside what the device-side planner handles    */
 } rb_status;
 
 /* Human-readable text for a return code of any function below (rb_status or cudaError_t). */
@@ -122,13 +123,19 @@ RB_API int rb_ssi(const float* x, const int32_t* len, int B, int ld, const rb_pl
 RB_API int rb_process(int algo, const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y,
                void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- host-buffer entry point (what a non-torch caller binds; used for the end-to-end measurement) ------
- * A context owns one stream, pinned staging and device scratch on `device`, grown on demand and reused.
- * rb_process_host: every pointer (x, len, y and all plan fields) is a HOST pointer; copies host->device,
- * runs rb_process, copies y back and returns when y is complete. */
+/* ---- host-buffer entry points (what a non-torch caller binds; used for the end-to-end measurement) -----
+ * A context owns four streams and three device slots on `device`, grown on demand and reused. A batch is cut into
+ * chunks (default: four utterances per SM, rb_ctx_set_chunk to change) that flow through a three-stage pipeline --
+ * host->device copy | plan + kernels | device->host copy -- ordered by events only, so PCIe in both directions and
+ * the SMs work at the same time; the call returns when y is complete. Page-locked x / y (and plan arrays) make
+ * the copies asynchronous; pageable memory works but serialises them.
+ * rb_process_host: every pointer (x, len, y and all plan fields) is a HOST pointer; the CSR plan is sliced per chunk.
+ * rb_process_host_seeded: no plan at all -- np.random.seed(seeds[u]) precedes utterance u and the plans are drawn on
+ * the device (rb_devplan_draw) while the previous chunk is being filtered. */
 typedef struct rb_ctx rb_ctx;
 RB_API int rb_ctx_create(rb_ctx** out, int device);
 RB_API int rb_ctx_destroy(rb_ctx* ctx);
+RB_API int rb_ctx_set_chunk(rb_ctx* ctx, int utterances /* 0 = default */);
 RB_API int rb_process_host(rb_ctx* ctx, int algo, const float* x, const int32_t* len, int B, int ld,
                     const rb_plan* plan, float* y);
 /* bytes moved by the last rb_process_host call: host->device and device->host */
@@ -162,6 +169,21 @@ RB_API int rb_planner_destroy(rb_planner* planner);
  * pass it to rb_process_host. */
 RB_API int rb_planner_draw(rb_planner* planner, const rb_args* args, int algo, int B, int ld, const int32_t* len,
                            const uint32_t* seeds, rb_rng_state* state, rb_plan* view);
+
+/* ---- device-side plan drawing for independently seeded utterances -------------------------------------------------
+ * Replays numpy's legacy MT19937 stream on the GPU (seeding, uniform, permutation, rand, normal -- the calls of
+ * RawBoost.py:15,79,80,90) and designs the notch cascades of genNotchCoeffs (RawBoost.py:28-48) there, so a seeded batch
+ * needs no host work and no plan upload: np.random.seed(seeds[u]) precedes utterance u, as in rb_planner_draw.
+ * Tap counts, impulse counts / positions and the float64 impulse gains are bit-identical to numpy's; float32 taps and
+ * SSI noise agree to 1 ulp. len / seeds are DEVICE arrays; `storage` is device memory of rb_devplan_bytes() bytes,
+ * 256-byte aligned; *plan (a HOST struct) receives device pointers into it, valid after the stream reaches this point.
+ * Limits (RB_ERR_UNSUPPORTED otherwise): ld <= 65536 when the algo uses ISD; cascades of at most 1024 taps. */
+RB_API size_t rb_devplan_bytes(const rb_args* args, int algo, int B, int ld);
+RB_API int rb_devplan_draw(const rb_args* args, int algo, int B, int ld, const int32_t* len, const uint32_t* seeds,
+                           void* storage, size_t storage_bytes, rb_plan* plan, void* stream);
+/* host buffers in, host buffers out, plans drawn on the device (see the host-buffer section above) */
+RB_API int rb_process_host_seeded(rb_ctx* ctx, int algo, const rb_args* args, const float* x, const int32_t* len,
+                                  const uint32_t* seeds, int B, int ld, float* y);
 
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------------------
  * rb_probe_fp32: runs a register-resident FFMA2 (packed=1) or FFMA (packed=0) chain on every SM and

@@ -18,7 +18,8 @@ SYMBOLS = (
     "rb_error_string", "rb_abi_version", "rb_workspace_bytes", "rb_filter_fir", "rb_normwav", "rb_lnl", "rb_isd",
     "rb_ssi", "rb_process", "rb_ctx_create", "rb_ctx_destroy", "rb_process_host", "rb_ctx_last_traffic",
     "rb_probe_fp32", "rb_launch_count", "rb_profile_enable", "rb_profile_read", "rb_planner_create", "rb_planner_destroy",
-    "rb_planner_draw",
+    "rb_planner_draw", "rb_devplan_bytes", "rb_devplan_draw", "rb_process_host_seeded",
+    "rb_ctx_set_chunk",
 )
 
 
@@ -53,6 +54,17 @@ class RbArgs(C.Structure):
 class RbRngState(C.Structure):
     """``struct rb_rng_state``: numpy's legacy MT19937 state."""
     _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int32), ("has_gauss", C.c_int32), ("cached_gaussian", C.c_double)]
+
+
+def args_struct(args, sr) -> RbArgs:
+    """``rb_args`` from the reference's argparse namespace (main.py:258-298) and the sample rate."""
+    s = RbArgs()
+    s.N_f, s.nBands = int(args.N_f), int(args.nBands)
+    for name in ("minF", "maxF", "minBW", "maxBW", "minCoeff", "maxCoeff", "minG", "maxG", "minBiasLinNonLin", "maxBiasLinNonLin",
+                 "P", "g_sd", "SNRmin", "SNRmax"):
+        setattr(s, name, float(getattr(args, name)))
+    s.fs = float(sr)
+    return s
 
 
 _lib = None
@@ -113,6 +125,14 @@ def load() -> C.CDLL:
     lib.rb_planner_destroy.argtypes = [vp]
     lib.rb_planner_draw.restype = i32
     lib.rb_planner_draw.argtypes = [vp, C.POINTER(RbArgs), i32, i32, i32, vp, vp, C.POINTER(RbRngState), C.POINTER(RbPlan)]
+    lib.rb_ctx_set_chunk.restype = i32
+    lib.rb_ctx_set_chunk.argtypes = [vp, i32]
+    lib.rb_process_host_seeded.restype = i32
+    lib.rb_process_host_seeded.argtypes = [vp, i32, C.POINTER(RbArgs), vp, vp, vp, i32, i32, vp]
+    lib.rb_devplan_bytes.restype = sz
+    lib.rb_devplan_bytes.argtypes = [C.POINTER(RbArgs), i32, i32, i32]
+    lib.rb_devplan_draw.restype = i32
+    lib.rb_devplan_draw.argtypes = [C.POINTER(RbArgs), i32, i32, i32, vp, vp, vp, sz, C.POINTER(RbPlan), vp]
     if lib.rb_abi_version() != RB_ABI_VERSION:
         raise RawBoostLibraryError(f"ABI mismatch: library {lib.rb_abi_version()}, binding {RB_ABI_VERSION}; rebuild")
     _lib = lib

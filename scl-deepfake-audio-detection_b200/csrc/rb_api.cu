@@ -3,6 +3,8 @@
 // (/root/reference/datautils/asvspoof_2019_augall_3.py:377-439).
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
+#include <initializer_list>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -200,6 +202,7 @@ const char* rb_error_string(int code) {
     case RB_ERR_WORKSPACE: return "rawboost_b200: workspace missing or smaller than rb_workspace_bytes()";
     case RB_ERR_NO_DEVICE: return "rawboost_b200: no usable CUDA device (needs compute capability 10.0)";
     case RB_ERR_PLAN: return "rawboost_b200: a plan field required by this algo is NULL";
+    case RB_ERR_UNSUPPORTED: return "rawboost_b200: arguments outside what the device-side planner supports (ld <= 65536 with ISD, cascades <= 1024 taps)";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -305,16 +308,200 @@ int rb_process(int algo, const float* x, const int32_t* len, int B, int ld, cons
   return RB_ERR_INVALID_ARG;
 }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------------------------------------------
-// host-buffer context
+// host-buffer context: a chunked three-stage pipeline (H2D | plan + kernels | D2H)
 // ---------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kSlots = 3;
+
+struct Slot {
+  char* dev = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t ev_in = nullptr, ev_planned = nullptr, ev_done = nullptr, ev_out = nullptr;
+};
+}  // namespace
+
 struct rb_ctx {
   int device;
-  cudaStream_t stream;
-  char* dev;          // one device arena, grown on demand
-  size_t dev_bytes;
+  int sm_count;
+  int chunk;  // utterances per pipeline chunk (0: four per SM)
+  cudaStream_t s_in, s_plan, s_cmp, s_out;
+  Slot slot[kSlots];
+  char* meta = nullptr;  // per-call device copy of len[] and seeds[]
+  size_t meta_bytes = 0;
   uint64_t h2d, d2h;
 };
+
+namespace {
+
+int slot_reserve(Slot& sl, size_t need) {
+  if (need <= sl.bytes) return RB_OK;
+  if (sl.dev) RB_CUDA(cudaFree(sl.dev));
+  sl.dev = nullptr;
+  sl.bytes = 0;
+  need += need / 8;
+  RB_CUDA(cudaMalloc((void**)&sl.dev, need));
+  sl.bytes = need;
+  return RB_OK;
+}
+
+struct Take {
+  size_t off = 0;
+  size_t operator()(size_t n) {
+    const size_t r = off;
+    off += align_up(n, 256);
+    return r;
+  }
+};
+
+// Common driver. plan != NULL: host CSR plan, sliced and uploaded per chunk. plan == NULL: seeds/args given, drawn on the device.
+int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, const rb_args* args,
+                 const uint32_t* seeds, float* y) {
+  RB_CUDA(cudaSetDevice(c->device));
+  const bool active = algo >= 1 && algo <= 8;
+  const bool use_lnl = (algo == 1 || algo == 4 || algo == 5 || algo == 6 || algo == 8);
+  const bool use_isd = (algo == 2 || algo == 4 || algo == 5 || algo == 7 || algo == 8);
+  const bool use_ssi = (algo == 3 || algo == 4 || algo == 6 || algo == 7);
+  const bool devplan = active && plan == nullptr;
+  if (active && !devplan) {
+    if (use_lnl && (plan->n_f < 1 || !plan->lnl_taps || !plan->lnl_tap_off)) return RB_ERR_PLAN;
+    if (use_isd && (!plan->isd_off || !plan->isd_idx || !plan->isd_fr)) return RB_ERR_PLAN;
+    if (use_ssi && (!plan->ssi_noise || !plan->ssi_taps || !plan->ssi_tap_off || !plan->ssi_snr_db)) return RB_ERR_PLAN;
+  }
+  if (devplan && (!args || !seeds)) return RB_ERR_INVALID_ARG;
+  const int chunk = std::max(1, std::min(B, c->chunk > 0 ? c->chunk : 4 * c->sm_count));
+  const int n_f = plan ? plan->n_f : (args ? args->N_f : 0);
+
+  // everything queued below is ordered by events only; the host blocks once, at the end
+  // per-call metadata: lengths (+ seeds) for the whole batch
+  const size_t meta_need = align_up((size_t)B * 4, 256) * 2;
+  if (meta_need > c->meta_bytes) {
+    RB_CUDA(cudaDeviceSynchronize());
+    if (c->meta) RB_CUDA(cudaFree(c->meta));
+    c->meta = nullptr;
+    c->meta_bytes = 0;
+    RB_CUDA(cudaMalloc((void**)&c->meta, meta_need));
+    c->meta_bytes = meta_need;
+  }
+  int32_t* d_len = (int32_t*)c->meta;
+  uint32_t* d_seeds = (uint32_t*)(c->meta + align_up((size_t)B * 4, 256));
+  uint64_t h2d = 0, d2h = 0;
+  RB_CUDA(cudaMemcpyAsync(d_len, len, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
+  h2d += (size_t)B * 4;
+  if (devplan) {
+    RB_CUDA(cudaMemcpyAsync(d_seeds, seeds, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
+    h2d += (size_t)B * 4;
+  }
+
+  // slot layout for the largest chunk
+  const size_t wave = (size_t)chunk * ld * sizeof(float);
+  const size_t ws_bytes = active ? rb_workspace_bytes(chunk, ld) : 0;
+  const size_t dp_bytes = devplan ? rb_devplan_bytes(args, algo, chunk, ld) : 0;
+  if (devplan && dp_bytes == 0) return RB_ERR_UNSUPPORTED;
+  size_t max_lt = 0, max_isd = 0, max_st = 0;  // largest per-chunk CSR payloads of a host plan
+  if (active && !devplan) {
+    for (int u0 = 0; u0 < B; u0 += chunk) {
+      const int bc = std::min(chunk, B - u0);
+      if (use_lnl) max_lt = std::max(max_lt, (size_t)(plan->lnl_tap_off[(size_t)(u0 + bc) * n_f] - plan->lnl_tap_off[(size_t)u0 * n_f]));
+      if (use_isd) max_isd = std::max(max_isd, (size_t)(plan->isd_off[u0 + bc] - plan->isd_off[u0]));
+      if (use_ssi) max_st = std::max(max_st, (size_t)(plan->ssi_tap_off[u0 + bc] - plan->ssi_tap_off[u0]));
+    }
+  }
+  Take take;
+  const size_t o_x = take(wave), o_y = take(wave), o_ws = take(ws_bytes), o_dp = take(dp_bytes);
+  const size_t o_lo = take(use_lnl && !devplan ? ((size_t)chunk * n_f + 1) * 4 : 0), o_lt = take(max_lt * 4);
+  const size_t o_io = take(use_isd && !devplan ? (size_t)(chunk + 1) * 4 : 0), o_ii = take(max_isd * 4), o_if = take(max_isd * 8);
+  const size_t o_sn = take(use_ssi && !devplan ? wave : 0), o_so = take(use_ssi && !devplan ? (size_t)(chunk + 1) * 4 : 0),
+               o_st = take(max_st * 4), o_sr = take(use_ssi && !devplan ? (size_t)chunk * 4 : 0);
+  const int nchunks = (B + chunk - 1) / chunk;
+  for (int k = 0; k < std::min(kSlots, nchunks); ++k) {
+    if (take.off > c->slot[k].bytes) {
+      RB_CUDA(cudaDeviceSynchronize());
+      RB_TRY(slot_reserve(c->slot[k], take.off));
+    }
+  }
+
+  for (int ci = 0; ci < nchunks; ++ci) {
+    Slot& sl = c->slot[ci % kSlots];
+    char* d = sl.dev;
+    const int u0 = ci * chunk, bc = std::min(chunk, B - u0);
+    const size_t cw = (size_t)bc * ld * sizeof(float);
+    // ---- stage 1: host -> device ------------------------------------------------------------------------------------
+    if (ci >= kSlots) RB_CUDA(cudaStreamWaitEvent(c->s_in, sl.ev_out, 0));  // the slot's previous chunk has left the device
+    RB_CUDA(cudaMemcpyAsync(d + o_x, x + (size_t)u0 * ld, cw, cudaMemcpyHostToDevice, c->s_in));
+    h2d += cw;
+    rb_plan dp;
+    memset(&dp, 0, sizeof(dp));
+    if (active && !devplan) {
+      dp.n_f = plan->n_f;
+      dp.g_sd = plan->g_sd;
+      auto up = [&](size_t o, const void* src, size_t n) -> int {
+        if (n == 0) return RB_OK;
+        h2d += n;
+        return (int)cudaMemcpyAsync(d + o, src, n, cudaMemcpyHostToDevice, c->s_in);
+      };
+      // CSR slices keep their absolute offsets; the value pointers are rebased so that ptr[off] lands in the slice
+      if (use_lnl) {
+        const int32_t* off = plan->lnl_tap_off + (size_t)u0 * n_f;
+        const size_t base = (size_t)off[0], cnt = (size_t)off[(size_t)bc * n_f] - base;
+        RB_TRY(up(o_lo, off, ((size_t)bc * n_f + 1) * 4));
+        RB_TRY(up(o_lt, plan->lnl_taps + base, cnt * 4));
+        dp.lnl_tap_off = (const int32_t*)(d + o_lo);
+        dp.lnl_taps = (const float*)(d + o_lt) - base;
+      }
+      if (use_isd) {
+        const int32_t* off = plan->isd_off + u0;
+        const size_t base = (size_t)off[0], cnt = (size_t)off[bc] - base;
+        RB_TRY(up(o_io, off, (size_t)(bc + 1) * 4));
+        RB_TRY(up(o_ii, plan->isd_idx + base, cnt * 4));
+        RB_TRY(up(o_if, plan->isd_fr + base, cnt * 8));
+        dp.isd_off = (const int32_t*)(d + o_io);
+        dp.isd_idx = (const int32_t*)(d + o_ii) - base;
+        dp.isd_fr = (const double*)(d + o_if) - base;
+      }
+      if (use_ssi) {
+        const int32_t* off = plan->ssi_tap_off + u0;
+        const size_t base = (size_t)off[0], cnt = (size_t)off[bc] - base;
+        RB_TRY(up(o_sn, plan->ssi_noise + (size_t)u0 * ld, cw));
+        RB_TRY(up(o_so, off, (size_t)(bc + 1) * 4));
+        RB_TRY(up(o_st, plan->ssi_taps + base, cnt * 4));
+        RB_TRY(up(o_sr, plan->ssi_snr_db + u0, (size_t)bc * 4));
+        dp.ssi_noise = (const float*)(d + o_sn);
+        dp.ssi_tap_off = (const int32_t*)(d + o_so);
+        dp.ssi_taps = (const float*)(d + o_st) - base;
+        dp.ssi_snr_db = (const float*)(d + o_sr);
+      }
+    }
+    RB_CUDA(cudaEventRecord(sl.ev_in, c->s_in));
+    // ---- stage 2: plan (own stream, overlaps the previous chunk's kernels) + kernels --------------------------------------
+    if (devplan) {
+      RB_CUDA(cudaStreamWaitEvent(c->s_plan, sl.ev_in, 0));
+      RB_TRY(rb_devplan_draw(args, algo, bc, ld, d_len + u0, d_seeds + u0, d + o_dp, dp_bytes, &dp, c->s_plan));
+      RB_CUDA(cudaEventRecord(sl.ev_planned, c->s_plan));
+      RB_CUDA(cudaStreamWaitEvent(c->s_cmp, sl.ev_planned, 0));
+    } else {
+      RB_CUDA(cudaStreamWaitEvent(c->s_cmp, sl.ev_in, 0));
+    }
+    RB_TRY(rb_process(algo, (const float*)(d + o_x), d_len + u0, bc, ld, active ? &dp : nullptr, (float*)(d + o_y), d + o_ws, ws_bytes,
+                      c->s_cmp));
+    RB_CUDA(cudaEventRecord(sl.ev_done, c->s_cmp));
+    // ---- stage 3: device -> host -------------------------------------------------------------------------------------
+    RB_CUDA(cudaStreamWaitEvent(c->s_out, sl.ev_done, 0));
+    RB_CUDA(cudaMemcpyAsync(y + (size_t)u0 * ld, d + o_y, cw, cudaMemcpyDeviceToHost, c->s_out));
+    d2h += cw;
+    RB_CUDA(cudaEventRecord(sl.ev_out, c->s_out));
+  }
+  RB_CUDA(cudaStreamSynchronize(c->s_out));
+  c->h2d = h2d;
+  c->d2h = d2h;
+  return RB_OK;
+}
+
+}  // namespace
+
+extern "C" {
 
 int rb_ctx_create(rb_ctx** out, int device) {
   if (!out) return RB_ERR_INVALID_ARG;
@@ -327,12 +514,18 @@ int rb_ctx_create(rb_ctx** out, int device) {
   rb_ctx* c = new (std::nothrow) rb_ctx();
   if (!c) return RB_ERR_INVALID_ARG;
   c->device = device;
-  c->dev = nullptr;
-  c->dev_bytes = 0;
+  c->sm_count = prop.multiProcessorCount;
+  c->chunk = 0;
   c->h2d = c->d2h = 0;
-  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  c->s_in = c->s_plan = c->s_cmp = c->s_out = nullptr;
+  cudaError_t e = cudaSuccess;
+  for (cudaStream_t* s : {&c->s_in, &c->s_plan, &c->s_cmp, &c->s_out})
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+  for (Slot& sl : c->slot)
+    for (cudaEvent_t* ev : {&sl.ev_in, &sl.ev_planned, &sl.ev_done, &sl.ev_out})
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   if (e != cudaSuccess) {
-    delete c;
+    rb_ctx_destroy(c);
     return (int)e;
   }
   *out = c;
@@ -342,10 +535,22 @@ int rb_ctx_create(rb_ctx** out, int device) {
 int rb_ctx_destroy(rb_ctx* c) {
   if (!c) return RB_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  if (c->dev) cudaFree(c->dev);
-  cudaStreamDestroy(c->stream);
+  cudaDeviceSynchronize();
+  for (Slot& sl : c->slot) {
+    if (sl.dev) cudaFree(sl.dev);
+    for (cudaEvent_t ev : {sl.ev_in, sl.ev_planned, sl.ev_done, sl.ev_out})
+      if (ev) cudaEventDestroy(ev);
+  }
+  if (c->meta) cudaFree(c->meta);
+  for (cudaStream_t s : {c->s_in, c->s_plan, c->s_cmp, c->s_out})
+    if (s) cudaStreamDestroy(s);
   delete c;
+  return RB_OK;
+}
+
+int rb_ctx_set_chunk(rb_ctx* c, int utterances) {
+  if (!c || utterances < 0) return RB_ERR_INVALID_ARG;
+  c->chunk = utterances;
   return RB_OK;
 }
 
@@ -356,95 +561,28 @@ int rb_ctx_last_traffic(const rb_ctx* c, uint64_t* h2d, uint64_t* d2h) {
   return RB_OK;
 }
 
-int rb_process_host(rb_ctx* c, int algo, const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y) {
+static int check_host_batch(const rb_ctx* c, const float* x, const int32_t* len, int B, int ld, const float* y) {
   if (!c) return RB_ERR_INVALID_ARG;
   if (B < 0 || ld < 0) return RB_ERR_INVALID_ARG;
   if (B == 0 || ld == 0) return RB_OK;
   if (!x || !len || !y) return RB_ERR_INVALID_ARG;
   if (ld % 4 != 0) return RB_ERR_ALIGNMENT;
-  RB_CUDA(cudaSetDevice(c->device));
-  const bool use_lnl = (algo == 1 || algo == 4 || algo == 5 || algo == 6 || algo == 8);
-  const bool use_isd = (algo == 2 || algo == 4 || algo == 5 || algo == 7 || algo == 8);
-  const bool use_ssi = (algo == 3 || algo == 4 || algo == 6 || algo == 7);
-  if ((use_lnl || use_isd || use_ssi) && !plan) return RB_ERR_PLAN;
-  if (use_lnl && (plan->n_f < 1 || !plan->lnl_taps || !plan->lnl_tap_off)) return RB_ERR_PLAN;
-  if (use_isd && (!plan->isd_off || !plan->isd_idx || !plan->isd_fr)) return RB_ERR_PLAN;
-  if (use_ssi && (!plan->ssi_noise || !plan->ssi_taps || !plan->ssi_tap_off || !plan->ssi_snr_db)) return RB_ERR_PLAN;
-
-  const size_t wave = (size_t)B * ld * sizeof(float);
-  const size_t n_lnl_off = use_lnl ? (size_t)B * plan->n_f + 1 : 0;
-  const size_t n_lnl_taps = use_lnl ? (size_t)plan->lnl_tap_off[n_lnl_off - 1] : 0;
-  const size_t n_isd = use_isd ? (size_t)plan->isd_off[B] : 0;
-  const size_t n_ssi_taps = use_ssi ? (size_t)plan->ssi_tap_off[B] : 0;
-
-  // arena layout
-  size_t off = 0;
-  auto take = [&](size_t n) {
-    size_t r = off;
-    off += align_up(n, 256);
-    return r;
-  };
-  const size_t o_x = take(wave), o_y = take(wave), o_len = take((size_t)B * 4);
-  const size_t o_lo = take(n_lnl_off * 4), o_lt = take(n_lnl_taps * 4);
-  const size_t o_io = take(use_isd ? (size_t)(B + 1) * 4 : 0), o_ii = take(n_isd * 4), o_if = take(n_isd * 8);
-  const size_t o_sn = take(use_ssi ? wave : 0), o_so = take(use_ssi ? (size_t)(B + 1) * 4 : 0), o_st = take(n_ssi_taps * 4),
-               o_sr = take(use_ssi ? (size_t)B * 4 : 0);
-  const size_t ws_bytes = rb_workspace_bytes(B, ld);
-  const size_t o_ws = take(ws_bytes);
-  if (off > c->dev_bytes) {
-    RB_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->dev) RB_CUDA(cudaFree(c->dev));
-    c->dev = nullptr;
-    c->dev_bytes = 0;
-    RB_CUDA(cudaMalloc((void**)&c->dev, off));
-    c->dev_bytes = off;
-  }
-  char* d = c->dev;
-  cudaStream_t st = c->stream;
-  uint64_t h2d = 0;
-  auto up = [&](size_t o, const void* src, size_t n) -> int {
-    if (n == 0) return RB_OK;
-    h2d += n;
-    return (int)cudaMemcpyAsync(d + o, src, n, cudaMemcpyHostToDevice, st);
-  };
-  RB_TRY(up(o_x, x, wave));
-  RB_TRY(up(o_len, len, (size_t)B * 4));
-  rb_plan dp;
-  memset(&dp, 0, sizeof(dp));
-  if (plan) {
-    dp.n_f = plan->n_f;
-    dp.g_sd = plan->g_sd;
-  }
-  if (use_lnl) {
-    RB_TRY(up(o_lo, plan->lnl_tap_off, n_lnl_off * 4));
-    RB_TRY(up(o_lt, plan->lnl_taps, n_lnl_taps * 4));
-    dp.lnl_tap_off = (const int32_t*)(d + o_lo);
-    dp.lnl_taps = (const float*)(d + o_lt);
-  }
-  if (use_isd) {
-    RB_TRY(up(o_io, plan->isd_off, (size_t)(B + 1) * 4));
-    RB_TRY(up(o_ii, plan->isd_idx, n_isd * 4));
-    RB_TRY(up(o_if, plan->isd_fr, n_isd * 8));
-    dp.isd_off = (const int32_t*)(d + o_io);
-    dp.isd_idx = (const int32_t*)(d + o_ii);
-    dp.isd_fr = (const double*)(d + o_if);
-  }
-  if (use_ssi) {
-    RB_TRY(up(o_sn, plan->ssi_noise, wave));
-    RB_TRY(up(o_so, plan->ssi_tap_off, (size_t)(B + 1) * 4));
-    RB_TRY(up(o_st, plan->ssi_taps, n_ssi_taps * 4));
-    RB_TRY(up(o_sr, plan->ssi_snr_db, (size_t)B * 4));
-    dp.ssi_noise = (const float*)(d + o_sn);
-    dp.ssi_tap_off = (const int32_t*)(d + o_so);
-    dp.ssi_taps = (const float*)(d + o_st);
-    dp.ssi_snr_db = (const float*)(d + o_sr);
-  }
-  RB_TRY(rb_process(algo, (const float*)(d + o_x), (const int32_t*)(d + o_len), B, ld, &dp, (float*)(d + o_y), d + o_ws, ws_bytes, st));
-  RB_CUDA(cudaMemcpyAsync(y, d + o_y, wave, cudaMemcpyDeviceToHost, st));
-  RB_CUDA(cudaStreamSynchronize(st));
-  c->h2d = h2d;
-  c->d2h = wave;
   return RB_OK;
+}
+
+int rb_process_host(rb_ctx* c, int algo, const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y) {
+  RB_TRY(check_host_batch(c, x, len, B, ld, y));
+  if (B == 0 || ld == 0) return RB_OK;
+  if (algo >= 1 && algo <= 8 && !plan) return RB_ERR_PLAN;
+  return run_pipeline(c, algo, x, len, B, ld, plan, nullptr, nullptr, y);
+}
+
+int rb_process_host_seeded(rb_ctx* c, int algo, const rb_args* args, const float* x, const int32_t* len, const uint32_t* seeds, int B,
+                           int ld, float* y) {
+  RB_TRY(check_host_batch(c, x, len, B, ld, y));
+  if (B == 0 || ld == 0) return RB_OK;
+  if (algo >= 1 && algo <= 8 && (!args || !seeds)) return RB_ERR_INVALID_ARG;
+  return run_pipeline(c, algo, x, len, B, ld, nullptr, args, seeds, y);
 }
 
 }  // extern "C"

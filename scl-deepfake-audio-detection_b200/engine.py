@@ -75,6 +75,51 @@ class Engine:
             setattr(s, name, None if v is None else v.data_ptr())
         return DevicePlan(B=plan.B, ld=plan.ld, lengths=lengths, tensors=t, struct=s, host=plan)
 
+    def draw_device_plan(self, lengths: torch.Tensor, seeds, sr, args, algo: int, ld: int) -> DevicePlan:
+        """Draw the plans of a seeded batch ON THE DEVICE (``rb_devplan_draw``): ``np.random.seed(seeds[u])`` precedes
+        utterance u, exactly as ``plans.draw_batch(..., seeds=...)`` / ``NativePlanner.draw`` do on the host. Asynchronous on
+        torch's current stream; the returned plan's arrays live in one device buffer owned by the plan."""
+        B = int(lengths.numel())
+        if not torch.is_tensor(seeds):
+            seeds = torch.from_numpy(np.ascontiguousarray(seeds, dtype=np.uint32).view(np.int32)).to(self.device)
+        a = _lib.args_struct(args, sr)
+        need = int(self.lib.rb_devplan_bytes(C.byref(a), int(algo), B, int(ld)))
+        store = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        s = _lib.RbPlan()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.rb_devplan_draw(C.byref(a), int(algo), B, int(ld), _ptr(lengths), _ptr(seeds), C.c_void_p(self._ws_ptr(store)),
+                                          need, C.byref(s), C.c_void_p(stream))
+        _lib.check(rc, f"rb_devplan_draw(algo={algo})")
+        return DevicePlan(B=B, ld=int(ld), lengths=lengths, tensors={"storage": store, "seeds": seeds}, struct=s, host=None)
+
+    def download_plan(self, dp: DevicePlan) -> BatchPlan:
+        """Copy a device-drawn plan back to the host (tests / inspection)."""
+        store = dp.tensors["storage"]
+
+        def fetch(ptr, count, dtype):
+            if not ptr or count == 0:
+                return np.zeros(0, dtype=dtype)
+            off = int(ptr) - store.data_ptr()
+            return store[off:off + count * np.dtype(dtype).itemsize].cpu().numpy().view(dtype).copy()
+
+        s, B, ld = dp.struct, dp.B, dp.ld
+        bp = BatchPlan(B=B, ld=ld, lengths=dp.lengths.cpu().numpy(), g_sd=float(s.g_sd))
+        if s.lnl_tap_off:
+            bp.n_f = int(s.n_f)
+            bp.lnl_tap_off = fetch(s.lnl_tap_off, B * bp.n_f + 1, np.int32)
+            bp.lnl_taps = fetch(s.lnl_taps, int(bp.lnl_tap_off[-1]), np.float32)
+        if s.isd_off:
+            bp.isd_off = fetch(s.isd_off, B + 1, np.int32)
+            bp.isd_idx = fetch(s.isd_idx, int(bp.isd_off[-1]), np.int32)
+            bp.isd_fr = fetch(s.isd_fr, int(bp.isd_off[-1]), np.float64)
+        if s.ssi_tap_off:
+            bp.ssi_noise = fetch(s.ssi_noise, B * ld, np.float32).reshape(B, ld)
+            bp.ssi_tap_off = fetch(s.ssi_tap_off, B + 1, np.int32)
+            bp.ssi_taps = fetch(s.ssi_taps, int(bp.ssi_tap_off[-1]), np.float32)
+            bp.ssi_snr_db = fetch(s.ssi_snr_db, B, np.float32)
+        return bp
+
     def pack_waveforms(self, waves: Sequence[np.ndarray], ld: Optional[int] = None):
         """Host list of 1-D float arrays -> ([B, ld] float32 device tensor, int32 lengths on device)."""
         lengths = np.array([int(w.shape[0]) for w in waves], dtype=np.int32)
@@ -141,10 +186,7 @@ class Engine:
     def process_host(self, algo: int, x: np.ndarray, plan: Optional[BatchPlan], out: Optional[np.ndarray] = None) -> np.ndarray:
         """x: [B, ld] float32 host array (pinned for asynchronous DMA); plan: host :class:`BatchPlan`.
         Copies in, computes, copies out; returns when ``out`` is complete."""
-        if self._ctx is None:
-            ctx = C.c_void_p()
-            _lib.check(self.lib.rb_ctx_create(C.byref(ctx), self.device.index or 0), "rb_ctx_create")
-            self._ctx = ctx
+        self._host_ctx()
         if x.dtype != np.float32 or x.ndim != 2 or not x.flags.c_contiguous:
             raise ValueError("x must be a C-contiguous [B, ld] float32 array")
         B, ld = x.shape
@@ -166,6 +208,37 @@ class Engine:
         rc = self.lib.rb_process_host(self._ctx, int(algo), C.c_void_p(x.ctypes.data), C.c_void_p(lengths.ctypes.data), B, ld,
                                       C.byref(s), C.c_void_p(out.ctypes.data))
         _lib.check(rc, f"rb_process_host(algo={algo})")
+        return out
+
+    def _host_ctx(self):
+        if self._ctx is None:
+            ctx = C.c_void_p()
+            _lib.check(self.lib.rb_ctx_create(C.byref(ctx), self.device.index or 0), "rb_ctx_create")
+            self._ctx = ctx
+        return self._ctx
+
+    def set_host_chunk(self, utterances: int) -> None:
+        """Utterances per pipeline chunk of the host-buffer entry points (0 = default: four per SM)."""
+        _lib.check(self.lib.rb_ctx_set_chunk(self._host_ctx(), int(utterances)), "rb_ctx_set_chunk")
+
+    def process_host_seeded(self, algo: int, x: np.ndarray, lengths: np.ndarray, seeds, sr, args,
+                            out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host waveforms in, host results out, plans drawn ON THE DEVICE from per-utterance seeds
+        (``np.random.seed(seeds[u])`` before utterance u). x: [B, ld] float32, page-locked for full overlap."""
+        if x.dtype != np.float32 or x.ndim != 2 or not x.flags.c_contiguous:
+            raise ValueError("x must be a C-contiguous [B, ld] float32 array")
+        B, ld = x.shape
+        if out is None:
+            out = np.zeros_like(x)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        if lengths.shape[0] != B or seeds.shape[0] != B:
+            raise ValueError("one length and one seed per utterance")
+        a = _lib.args_struct(args, sr)
+        rc = self.lib.rb_process_host_seeded(self._host_ctx(), int(algo), C.byref(a), C.c_void_p(x.ctypes.data),
+                                             C.c_void_p(lengths.ctypes.data), C.c_void_p(seeds.ctypes.data), B, ld,
+                                             C.c_void_p(out.ctypes.data))
+        _lib.check(rc, f"rb_process_host_seeded(algo={algo})")
         return out
 
     def last_host_traffic(self):

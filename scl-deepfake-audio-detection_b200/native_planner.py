@@ -17,14 +17,7 @@ from . import _lib
 from .plans import ALGO_USES_ISD, ALGO_USES_LNL, ALGO_USES_SSI, BatchPlan, padded_ld
 
 
-def _args_struct(args, sr) -> _lib.RbArgs:
-    s = _lib.RbArgs()
-    s.N_f, s.nBands = int(args.N_f), int(args.nBands)
-    for name in ("minF", "maxF", "minBW", "maxBW", "minCoeff", "maxCoeff", "minG", "maxG", "minBiasLinNonLin", "maxBiasLinNonLin",
-                 "P", "g_sd", "SNRmin", "SNRmax"):
-        setattr(s, name, float(getattr(args, name)))
-    s.fs = float(sr)
-    return s
+_args_struct = _lib.args_struct
 
 
 def _view(ptr, n, dtype):
