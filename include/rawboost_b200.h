@@ -138,6 +138,12 @@ RB_API int rb_ctx_destroy(rb_ctx* ctx);
 RB_API int rb_ctx_set_chunk(rb_ctx* ctx, int utterances /* 0 = default */);
 RB_API int rb_process_host(rb_ctx* ctx, int algo, const float* x, const int32_t* len, int B, int ld,
                     const rb_plan* plan, float* y);
+/* Tracing: with rb_ctx_trace(ctx, 1) every later call records, per pipeline chunk, six doubles -- first utterance, utterance
+ * count, and the milliseconds after the start of the call at which its copy-in, plan, kernels and copy-out finished (device
+ * time, CUDA events). rb_ctx_timeline copies up to `capacity` doubles of the last call and returns how many there are
+ * (>= 0; this one function does not return an rb_status on success). */
+RB_API int rb_ctx_trace(rb_ctx* ctx, int on);
+RB_API int rb_ctx_timeline(const rb_ctx* ctx, double* out, int capacity);
 /* bytes moved by the last rb_process_host call: host->device and device->host */
 RB_API int rb_ctx_last_traffic(const rb_ctx* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 

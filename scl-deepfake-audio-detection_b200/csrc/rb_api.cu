@@ -314,7 +314,7 @@ int rb_process(int algo, const float* x, const int32_t* len, int B, int ld, cons
 // host-buffer context: a chunked three-stage pipeline (H2D | plan + kernels | D2H)
 // ---------------------------------------------------------------------------------------------------
 namespace {
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 
 struct Slot {
   char* dev = nullptr;
@@ -328,10 +328,16 @@ struct rb_ctx {
   int sm_count;
   int chunk;  // utterances per pipeline chunk (0: four per SM)
   cudaStream_t s_in, s_plan, s_cmp, s_out;
+  cudaEvent_t ev_meta;
   Slot slot[kSlots];
   char* meta = nullptr;  // per-call device copy of len[] and seeds[]
   size_t meta_bytes = 0;
+  char* planmem = nullptr;  // device-drawn plans of the whole batch (rb_process_host_seeded)
+  size_t planmem_bytes = 0;
+  std::vector<cudaEvent_t> ev_planned;  // one per chunk
   uint64_t h2d, d2h;
+  int trace = 0;                 // rb_ctx_trace: record a per-chunk timeline of the next calls
+  std::vector<double> timeline;  // per chunk: first utterance, utterances, ms at which copy-in / plan / kernels / copy-out ended
 };
 
 namespace {
@@ -373,6 +379,10 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
   if (devplan && (!args || !seeds)) return RB_ERR_INVALID_ARG;
   const int chunk = std::max(1, std::min(B, c->chunk > 0 ? c->chunk : 4 * c->sm_count));
   const int n_f = plan ? plan->n_f : (args ? args->N_f : 0);
+  std::vector<int> first;  // first utterance of each chunk, plus B
+  for (int u = 0; u < B; u += chunk) first.push_back(u);
+  first.push_back(B);
+  const int nchunks = (int)first.size() - 1;
 
   // everything queued below is ordered by events only; the host blocks once, at the end
   // per-call metadata: lengths (+ seeds) for the whole batch
@@ -394,28 +404,43 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     RB_CUDA(cudaMemcpyAsync(d_seeds, seeds, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
     h2d += (size_t)B * 4;
   }
+  RB_CUDA(cudaEventRecord(c->ev_meta, c->s_in));
+  RB_CUDA(cudaStreamWaitEvent(c->s_plan, c->ev_meta, 0));
+  RB_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_meta, 0));
 
   // slot layout for the largest chunk
   const size_t wave = (size_t)chunk * ld * sizeof(float);
   const size_t ws_bytes = active ? rb_workspace_bytes(chunk, ld) : 0;
-  const size_t dp_bytes = devplan ? rb_devplan_bytes(args, algo, chunk, ld) : 0;
+  const size_t dp_bytes = devplan ? rb_devplan_bytes(args, algo, B, ld) : 0;
   if (devplan && dp_bytes == 0) return RB_ERR_UNSUPPORTED;
+  if (dp_bytes > c->planmem_bytes) {
+    RB_CUDA(cudaDeviceSynchronize());
+    if (c->planmem) RB_CUDA(cudaFree(c->planmem));
+    c->planmem = nullptr;
+    c->planmem_bytes = 0;
+    RB_CUDA(cudaMalloc((void**)&c->planmem, dp_bytes + dp_bytes / 8));
+    c->planmem_bytes = dp_bytes + dp_bytes / 8;
+  }
+  while (devplan && (int)c->ev_planned.size() < nchunks) {
+    cudaEvent_t e;
+    RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_planned.push_back(e);
+  }
   size_t max_lt = 0, max_isd = 0, max_st = 0;  // largest per-chunk CSR payloads of a host plan
   if (active && !devplan) {
-    for (int u0 = 0; u0 < B; u0 += chunk) {
-      const int bc = std::min(chunk, B - u0);
+    for (int ci = 0; ci < nchunks; ++ci) {
+      const int u0 = first[ci], bc = first[ci + 1] - u0;
       if (use_lnl) max_lt = std::max(max_lt, (size_t)(plan->lnl_tap_off[(size_t)(u0 + bc) * n_f] - plan->lnl_tap_off[(size_t)u0 * n_f]));
       if (use_isd) max_isd = std::max(max_isd, (size_t)(plan->isd_off[u0 + bc] - plan->isd_off[u0]));
       if (use_ssi) max_st = std::max(max_st, (size_t)(plan->ssi_tap_off[u0 + bc] - plan->ssi_tap_off[u0]));
     }
   }
   Take take;
-  const size_t o_x = take(wave), o_y = take(wave), o_ws = take(ws_bytes), o_dp = take(dp_bytes);
+  const size_t o_x = take(wave), o_y = take(wave), o_ws = take(ws_bytes);
   const size_t o_lo = take(use_lnl && !devplan ? ((size_t)chunk * n_f + 1) * 4 : 0), o_lt = take(max_lt * 4);
   const size_t o_io = take(use_isd && !devplan ? (size_t)(chunk + 1) * 4 : 0), o_ii = take(max_isd * 4), o_if = take(max_isd * 8);
   const size_t o_sn = take(use_ssi && !devplan ? wave : 0), o_so = take(use_ssi && !devplan ? (size_t)(chunk + 1) * 4 : 0),
                o_st = take(max_st * 4), o_sr = take(use_ssi && !devplan ? (size_t)chunk * 4 : 0);
-  const int nchunks = (B + chunk - 1) / chunk;
   for (int k = 0; k < std::min(kSlots, nchunks); ++k) {
     if (take.off > c->slot[k].bytes) {
       RB_CUDA(cudaDeviceSynchronize());
@@ -423,10 +448,45 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     }
   }
 
+  std::vector<cudaEvent_t> tev[5];  // trace: [0] start of the call, [1..4] per chunk: copy-in, plan, kernels, copy-out
+  auto mark = [&](int stage, cudaStream_t st) {
+    if (!c->trace) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, st);
+      tev[stage].push_back(e);
+    }
+  };
+  mark(0, c->s_in);
+  // Device planner: the plans need only lengths and seeds, so the planner stream runs ahead of the copies. The first chunk is
+  // planned on its own (the kernels can start as soon as its waveforms are in); the stream-replay stage of all other
+  // utterances is one launch (it is latency-bound: one warp per utterance, thousands in flight), after which each chunk only
+  // needs its swaps applied.
+  rb_plan whole;
+  memset(&whole, 0, sizeof(whole));
+  if (devplan) {
+    const int c0 = first[1];
+    RB_TRY(devplan_begin(args, algo, B, ld, d_len, d_seeds, c->planmem, c->planmem_bytes, &whole, c->s_plan));
+    if (use_ssi) {  // SSI tap offsets need the stream positions of every utterance
+      RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, c->planmem, 0, B, c->s_plan));
+      RB_TRY(devplan_end(args, algo, B, ld, c->planmem, c->s_plan));
+    } else {
+      RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, c->planmem, 0, c0, c->s_plan));
+    }
+    RB_TRY(devplan_apply(args, algo, B, ld, d_len, c->planmem, 0, c0, c->s_plan));
+    RB_CUDA(cudaEventRecord(c->ev_planned[0], c->s_plan));
+    mark(2, c->s_plan);
+    if (!use_ssi) RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, c->planmem, c0, B - c0, c->s_plan));
+    for (int ci = 1; ci < nchunks; ++ci) {
+      RB_TRY(devplan_apply(args, algo, B, ld, d_len, c->planmem, first[ci], first[ci + 1] - first[ci], c->s_plan));
+      RB_CUDA(cudaEventRecord(c->ev_planned[ci], c->s_plan));
+      mark(2, c->s_plan);
+    }
+  }
   for (int ci = 0; ci < nchunks; ++ci) {
     Slot& sl = c->slot[ci % kSlots];
     char* d = sl.dev;
-    const int u0 = ci * chunk, bc = std::min(chunk, B - u0);
+    const int u0 = first[ci], bc = first[ci + 1] - u0;
     const size_t cw = (size_t)bc * ld * sizeof(float);
     // ---- stage 1: host -> device ------------------------------------------------------------------------------------
     if (ci >= kSlots) RB_CUDA(cudaStreamWaitEvent(c->s_in, sl.ev_out, 0));  // the slot's previous chunk has left the device
@@ -475,25 +535,52 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
       }
     }
     RB_CUDA(cudaEventRecord(sl.ev_in, c->s_in));
+    mark(1, c->s_in);
     // ---- stage 2: plan (own stream, overlaps the previous chunk's kernels) + kernels --------------------------------------
-    if (devplan) {
-      RB_CUDA(cudaStreamWaitEvent(c->s_plan, sl.ev_in, 0));
-      RB_TRY(rb_devplan_draw(args, algo, bc, ld, d_len + u0, d_seeds + u0, d + o_dp, dp_bytes, &dp, c->s_plan));
-      RB_CUDA(cudaEventRecord(sl.ev_planned, c->s_plan));
-      RB_CUDA(cudaStreamWaitEvent(c->s_cmp, sl.ev_planned, 0));
-    } else {
-      RB_CUDA(cudaStreamWaitEvent(c->s_cmp, sl.ev_in, 0));
+    if (devplan) {  // the chunk's slice of the whole-batch plan: CSR offsets are absolute, so only the owner arrays move
+      dp = whole;
+      if (use_lnl) dp.lnl_tap_off = whole.lnl_tap_off + (size_t)u0 * n_f;
+      if (use_isd) dp.isd_off = whole.isd_off + u0;
+      if (use_ssi) {
+        dp.ssi_noise = whole.ssi_noise + (size_t)u0 * ld;
+        dp.ssi_tap_off = whole.ssi_tap_off + u0;
+        dp.ssi_snr_db = whole.ssi_snr_db + u0;
+      }
+      RB_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_planned[ci], 0));
     }
+    if (!devplan) mark(2, c->s_in);
+    RB_CUDA(cudaStreamWaitEvent(c->s_cmp, sl.ev_in, 0));
     RB_TRY(rb_process(algo, (const float*)(d + o_x), d_len + u0, bc, ld, active ? &dp : nullptr, (float*)(d + o_y), d + o_ws, ws_bytes,
                       c->s_cmp));
     RB_CUDA(cudaEventRecord(sl.ev_done, c->s_cmp));
+    mark(3, c->s_cmp);
     // ---- stage 3: device -> host -------------------------------------------------------------------------------------
     RB_CUDA(cudaStreamWaitEvent(c->s_out, sl.ev_done, 0));
     RB_CUDA(cudaMemcpyAsync(y + (size_t)u0 * ld, d + o_y, cw, cudaMemcpyDeviceToHost, c->s_out));
     d2h += cw;
     RB_CUDA(cudaEventRecord(sl.ev_out, c->s_out));
+    mark(4, c->s_out);
   }
   RB_CUDA(cudaStreamSynchronize(c->s_out));
+  if (c->trace) {
+    c->timeline.clear();
+    RB_CUDA(cudaDeviceSynchronize());
+    bool complete = tev[0].size() == 1;
+    for (int k = 1; k < 5; ++k) complete = complete && (int)tev[k].size() == nchunks;
+    if (complete) {
+      for (int ci = 0; ci < nchunks; ++ci) {
+        c->timeline.push_back((double)first[ci]);
+        c->timeline.push_back((double)(first[ci + 1] - first[ci]));
+        for (int k = 1; k < 5; ++k) {
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, tev[0][0], tev[k][ci]);
+          c->timeline.push_back((double)ms);
+        }
+      }
+    }
+    for (auto& v : tev)
+      for (cudaEvent_t e : v) cudaEventDestroy(e);
+  }
   c->h2d = h2d;
   c->d2h = d2h;
   return RB_OK;
@@ -518,9 +605,14 @@ int rb_ctx_create(rb_ctx** out, int device) {
   c->chunk = 0;
   c->h2d = c->d2h = 0;
   c->s_in = c->s_plan = c->s_cmp = c->s_out = nullptr;
-  cudaError_t e = cudaSuccess;
-  for (cudaStream_t* s : {&c->s_in, &c->s_plan, &c->s_cmp, &c->s_out})
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+  c->ev_meta = nullptr;
+  // copies and the (latency-bound, few-warp) planner kernels get priority over the FIR kernel's CTAs
+  int prio_lo = 0, prio_hi = 0;
+  cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  for (cudaStream_t* s : {&c->s_in, &c->s_plan, &c->s_out})
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->s_cmp, cudaStreamNonBlocking, prio_lo);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_meta, cudaEventDisableTiming);
   for (Slot& sl : c->slot)
     for (cudaEvent_t* ev : {&sl.ev_in, &sl.ev_planned, &sl.ev_done, &sl.ev_out})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -542,6 +634,9 @@ int rb_ctx_destroy(rb_ctx* c) {
       if (ev) cudaEventDestroy(ev);
   }
   if (c->meta) cudaFree(c->meta);
+  if (c->planmem) cudaFree(c->planmem);
+  for (cudaEvent_t e : c->ev_planned) cudaEventDestroy(e);
+  if (c->ev_meta) cudaEventDestroy(c->ev_meta);
   for (cudaStream_t s : {c->s_in, c->s_plan, c->s_cmp, c->s_out})
     if (s) cudaStreamDestroy(s);
   delete c;
@@ -552,6 +647,19 @@ int rb_ctx_set_chunk(rb_ctx* c, int utterances) {
   if (!c || utterances < 0) return RB_ERR_INVALID_ARG;
   c->chunk = utterances;
   return RB_OK;
+}
+
+int rb_ctx_trace(rb_ctx* c, int on) {
+  if (!c) return RB_ERR_INVALID_ARG;
+  c->trace = on ? 1 : 0;
+  return RB_OK;
+}
+
+int rb_ctx_timeline(const rb_ctx* c, double* out, int capacity) {
+  if (!c || capacity < 0 || (capacity > 0 && !out)) return RB_ERR_INVALID_ARG;
+  const int n = (int)std::min<size_t>(c->timeline.size(), (size_t)capacity);
+  for (int i = 0; i < n; ++i) out[i] = c->timeline[i];
+  return (int)c->timeline.size();
 }
 
 int rb_ctx_last_traffic(const rb_ctx* c, uint64_t* h2d, uint64_t* d2h) {

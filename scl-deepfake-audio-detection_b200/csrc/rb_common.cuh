@@ -91,4 +91,14 @@ int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const flo
                     int n_f, int pow_base, int pow_step, float* y, float* stats /*nullable*/,
                     const uint32_t* mask /*nullable*/, int mask_ld, cudaStream_t st);
 
+// Device-side planner, stage by stage (rb_devplan.cu); rb_devplan_draw runs all four for the whole batch. The pipelined host
+// entry interleaves stages 2/3 of one chunk with the kernels of the previous chunk.
+int devplan_begin(const rb_args* args, int algo, int B, int ld, const int32_t* len, const uint32_t* seeds, void* storage,
+                  size_t storage_bytes, rb_plan* plan, cudaStream_t st);
+int devplan_body(const rb_args* args, int algo, int B, int ld, const int32_t* len, const uint32_t* seeds, void* storage, int first,
+                 int count, cudaStream_t st);
+int devplan_apply(const rb_args* args, int algo, int B, int ld, const int32_t* len, void* storage, int first, int count,
+                  cudaStream_t st);
+int devplan_end(const rb_args* args, int algo, int B, int ld, void* storage, cudaStream_t st);
+
 }  // namespace rb

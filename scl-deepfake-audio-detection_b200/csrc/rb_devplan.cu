@@ -658,6 +658,22 @@ size_t rb_devplan_bytes(const rb_args* args, int algo, int B, int ld) {
 
 int rb_devplan_draw(const rb_args* args, int algo, int B, int ld, const int32_t* len, const uint32_t* seeds, void* storage,
                     size_t storage_bytes, rb_plan* plan, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = devplan_begin(args, algo, B, ld, len, seeds, storage, storage_bytes, plan, st);
+  if (rc != RB_OK || B == 0 || ld == 0) return rc;
+  if ((rc = devplan_body(args, algo, B, ld, len, seeds, storage, 0, B, st)) != RB_OK) return rc;
+  if ((rc = devplan_apply(args, algo, B, ld, len, storage, 0, B, st)) != RB_OK) return rc;
+  return devplan_end(args, algo, B, ld, storage, st);
+}
+
+}  // extern "C"
+
+namespace rb {
+
+// Stage 1: validation, first draws of every utterance, CSR offsets of the LnL taps and the impulses, LnL filter design.
+// Fills *plan with device pointers into `storage` (their contents are complete once all four stages have run).
+int devplan_begin(const rb_args* args, int algo, int B, int ld, const int32_t* len, const uint32_t* seeds, void* storage,
+                  size_t storage_bytes, rb_plan* plan, cudaStream_t st) {
   if (!args || !plan || B < 0 || ld < 0) return RB_ERR_INVALID_ARG;
   memset(plan, 0, sizeof(*plan));
   const bool lnl = (algo == 1 || algo == 4 || algo == 5 || algo == 6 || algo == 8);
@@ -674,12 +690,17 @@ int rb_devplan_draw(const rb_args* args, int algo, int B, int ld, const int32_t*
   const DevPlanLayout l = layout(*args, algo, B, ld);
   if (l.bytes > storage_bytes) return RB_ERR_WORKSPACE;
   char* d = (char*)storage;
-  cudaStream_t st = (cudaStream_t)stream;
   const int nl = lnl ? B * args->N_f : 0;
-
   plan_head_kernel<<<(B + kHeadWarps - 1) / kHeadWarps, 32 * kHeadWarps, 0, st>>>(
       *args, algo, B, len, seeds, (double*)(d + l.lnl_params), (int32_t*)(d + l.lnl_cnt), (int32_t*)(d + l.isd_cnt));
   RB_LAUNCH_CHECK();
+  if (isd) {
+    scan_kernel<<<1, 1024, 0, st>>>((const int32_t*)(d + l.isd_cnt), B, (int32_t*)(d + l.isd_off));
+    RB_LAUNCH_CHECK();
+    plan->isd_off = (const int32_t*)(d + l.isd_off);
+    plan->isd_idx = (const int32_t*)(d + l.isd_idx);
+    plan->isd_fr = (const double*)(d + l.isd_fr);
+  }
   if (lnl) {
     scan_kernel<<<1, 1024, 0, st>>>((const int32_t*)(d + l.lnl_cnt), nl, (int32_t*)(d + l.lnl_off));
     RB_LAUNCH_CHECK();
@@ -689,34 +710,7 @@ int rb_devplan_draw(const rb_args* args, int algo, int B, int ld, const int32_t*
     plan->lnl_taps = (const float*)(d + l.lnl_taps);
     plan->lnl_tap_off = (const int32_t*)(d + l.lnl_off);
   }
-  if (isd) {
-    scan_kernel<<<1, 1024, 0, st>>>((const int32_t*)(d + l.isd_cnt), B, (int32_t*)(d + l.isd_off));
-    RB_LAUNCH_CHECK();
-    plan->isd_off = (const int32_t*)(d + l.isd_off);
-    plan->isd_idx = (const int32_t*)(d + l.isd_idx);
-    plan->isd_fr = (const double*)(d + l.isd_fr);
-  }
-  if (isd || ssi) {
-    plan_body_kernel<<<(B + kBodyWarps - 1) / kBodyWarps, 32 * kBodyWarps, 0, st>>>(
-        *args, algo, B, ld, l.jld, len, seeds, (const int32_t*)(d + l.isd_off), (double*)(d + l.isd_fr), (uint16_t*)(d + l.isd_jseq),
-        (uint32_t*)(d + l.isd_cuts), l.cuts_ld, (float*)(d + l.ssi_noise), (double*)(d + l.ssi_params), (int32_t*)(d + l.ssi_cnt),
-        (float*)(d + l.ssi_snr));
-    RB_LAUNCH_CHECK();
-  }
-  if (isd) {
-    const size_t smem = 2 * kStageSteps * 2 + 2 * (kStageSteps / 32) * 4 + align_up((size_t)ld * 2 + 4, 16);
-    if (smem > 227 * 1024) return RB_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(perm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    perm_apply_kernel<<<B, 32, smem, st>>>(B, l.jld, len, (const uint16_t*)(d + l.isd_jseq), (const uint32_t*)(d + l.isd_cuts), l.cuts_ld,
-                                          (const int32_t*)(d + l.isd_off), (int32_t*)(d + l.isd_idx));
-    RB_LAUNCH_CHECK();
-  }
   if (ssi) {
-    scan_kernel<<<1, 1024, 0, st>>>((const int32_t*)(d + l.ssi_cnt), B, (int32_t*)(d + l.ssi_off));
-    RB_LAUNCH_CHECK();
-    design_kernel<<<B, kDesignThreads, 0, st>>>(args->nBands, args->fs, B, (const double*)(d + l.ssi_params),
-                                                (const int32_t*)(d + l.ssi_off), (float*)(d + l.ssi_taps));
-    RB_LAUNCH_CHECK();
     plan->ssi_noise = (const float*)(d + l.ssi_noise);
     plan->ssi_taps = (const float*)(d + l.ssi_taps);
     plan->ssi_tap_off = (const int32_t*)(d + l.ssi_off);
@@ -725,4 +719,53 @@ int rb_devplan_draw(const rb_args* args, int algo, int B, int ld, const int32_t*
   return RB_OK;
 }
 
-}  // extern "C"
+// Stage 2, utterances [first, first+count): the rest of the stream (swap targets and groups, impulse gains, SSI draws).
+int devplan_body(const rb_args* args, int algo, int B, int ld, const int32_t* len, const uint32_t* seeds, void* storage, int first,
+                 int count, cudaStream_t st) {
+  const bool isd = (algo == 2 || algo == 4 || algo == 5 || algo == 7 || algo == 8);
+  const bool ssi = (algo == 3 || algo == 4 || algo == 6 || algo == 7);
+  if (!(isd || ssi) || count <= 0) return RB_OK;
+  const DevPlanLayout l = layout(*args, algo, B, ld);
+  char* d = (char*)storage;
+  const size_t stride = 3 * (size_t)args->nBands + 1;
+  plan_body_kernel<<<(count + kBodyWarps - 1) / kBodyWarps, 32 * kBodyWarps, 0, st>>>(
+      *args, algo, count, ld, l.jld, len + first, seeds + first, (const int32_t*)(d + l.isd_off) + first, (double*)(d + l.isd_fr),
+      (uint16_t*)(d + l.isd_jseq) + (size_t)first * l.jld, (uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld,
+      (float*)(d + l.ssi_noise) + (size_t)first * ld, (double*)(d + l.ssi_params) + (size_t)first * stride,
+      (int32_t*)(d + l.ssi_cnt) + first, (float*)(d + l.ssi_snr) + first);
+  RB_LAUNCH_CHECK();
+  return RB_OK;
+}
+
+// Stage 3, utterances [first, first+count): apply the swaps, emit the impulse positions.
+int devplan_apply(const rb_args* args, int algo, int B, int ld, const int32_t* len, void* storage, int first, int count,
+                  cudaStream_t st) {
+  const bool isd = (algo == 2 || algo == 4 || algo == 5 || algo == 7 || algo == 8);
+  if (!isd || count <= 0) return RB_OK;
+  const DevPlanLayout l = layout(*args, algo, B, ld);
+  char* d = (char*)storage;
+  const size_t smem = 2 * kStageSteps * 2 + 2 * (kStageSteps / 32) * 4 + align_up((size_t)ld * 2 + 4, 16);
+  if (smem > 227 * 1024) return RB_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(perm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  perm_apply_kernel<<<count, 32, smem, st>>>(count, l.jld, len + first, (const uint16_t*)(d + l.isd_jseq) + (size_t)first * l.jld,
+                                            (const uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld,
+                                            (const int32_t*)(d + l.isd_off) + first, (int32_t*)(d + l.isd_idx));
+  RB_LAUNCH_CHECK();
+  return RB_OK;
+}
+
+// Stage 4 (after stage 2 of ALL utterances): CSR offsets and design of the SSI filters.
+int devplan_end(const rb_args* args, int algo, int B, int ld, void* storage, cudaStream_t st) {
+  const bool ssi = (algo == 3 || algo == 4 || algo == 6 || algo == 7);
+  if (!ssi || B <= 0) return RB_OK;
+  const DevPlanLayout l = layout(*args, algo, B, ld);
+  char* d = (char*)storage;
+  scan_kernel<<<1, 1024, 0, st>>>((const int32_t*)(d + l.ssi_cnt), B, (int32_t*)(d + l.ssi_off));
+  RB_LAUNCH_CHECK();
+  design_kernel<<<B, kDesignThreads, 0, st>>>(args->nBands, args->fs, B, (const double*)(d + l.ssi_params),
+                                              (const int32_t*)(d + l.ssi_off), (float*)(d + l.ssi_taps));
+  RB_LAUNCH_CHECK();
+  return RB_OK;
+}
+
+}  // namespace rb

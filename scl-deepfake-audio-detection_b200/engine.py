@@ -241,6 +241,20 @@ class Engine:
         _lib.check(rc, f"rb_process_host_seeded(algo={algo})")
         return out
 
+    def trace_host(self, on: bool) -> None:
+        """Record a per-chunk timeline of the following host-buffer calls (see :meth:`host_timeline`)."""
+        _lib.check(self.lib.rb_ctx_trace(self._host_ctx(), int(bool(on))), "rb_ctx_trace")
+
+    def host_timeline(self):
+        """Timeline of the last traced host-buffer call: one dict per pipeline chunk, times in ms from the call's start."""
+        n = self.lib.rb_ctx_timeline(self._host_ctx(), None, 0)
+        if n <= 0:
+            return []
+        buf = (C.c_double * n)()
+        self.lib.rb_ctx_timeline(self._host_ctx(), buf, n)
+        keys = ("first", "count", "copy_in_ms", "plan_ms", "kernels_ms", "copy_out_ms")
+        return [dict(zip(keys, buf[i:i + 6])) for i in range(0, n, 6)]
+
     def last_host_traffic(self):
         h2d, d2h = C.c_uint64(0), C.c_uint64(0)
         if self._ctx is not None:
