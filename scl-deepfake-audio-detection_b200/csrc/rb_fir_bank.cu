@@ -73,8 +73,10 @@ __device__ __forceinline__ void stage_x(float* __restrict__ dst, const float* __
 }
 
 // One filter segment: acc[r] += sum_i h[i] * src[t*kR + r + i + e0], taps already staged in he/ho (nbody*24 each).
+// ngroups = number of 4-tap groups that hold non-zero taps: full 24-tap bodies first, then a partial last body that stops
+// after its last useful group (uniform branch), so zero padding costs at most 3 taps + alignment instead of up to 23.
 __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __restrict__ src, const float* __restrict__ he,
-                                             const float* __restrict__ ho, int e0, int nbody) {
+                                             const float* __restrict__ ho, int e0, int ngroups) {
   float2 w[kWin / 2];
 #ifdef RB_WIN_LDS64
   // Window loads as 64-bit pairs: leaves ptxas free to keep every window pair in the register bank class the
@@ -100,9 +102,41 @@ __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __r
 #endif
   const float4* pe = reinterpret_cast<const float4*>(he);
   const float4* po = reinterpret_cast<const float4*>(ho);
-  for (int body = 0; body < nbody; ++body) {
+  constexpr int kGroups = kWin / 4;  // groups per unrolled body
+  const int nfull = ngroups / kGroups, glast = ngroups - nfull * kGroups;
+  for (int body = 0; body < nfull; ++body) {
 #pragma unroll
-    for (int g = 0; g < kWin / 4; ++g) {
+    for (int g = 0; g < kGroups; ++g) {
+      // the chunk that completes the window of this group lands in the slot freed by the previous group
+#ifdef RB_WIN_LDS64
+      w[((kR + 4 * g) % kWin) / 2] = lds64(xq);
+      w[((kR + 4 * g) % kWin) / 2 + 1] = lds64(xq + 2);
+      xq += 4;
+#else
+      const float4 v = *xq++;
+      w[((kR + 4 * g) % kWin) / 2] = make_float2(v.x, v.y);
+      w[((kR + 4 * g) % kWin) / 2 + 1] = make_float2(v.z, v.w);
+#endif
+      const float4 e = *pe++;
+      const float4 o = *po++;
+      const float2 e01 = make_float2(e.x, e.y), e23 = make_float2(e.z, e.w);
+      const float2 o01 = make_float2(o.x, o.y), o23 = make_float2(o.z, o.w);
+      // Tap-major order: ten consecutive FFMA2 share the tap operand, so it is served by the operand-reuse cache
+      // and every FFMA2 reads only two register pairs from the register file (three would halve... cost a third cycle).
+#pragma unroll
+      for (int r = 0; r < kR; r += 2) acc[r] = __ffma2_rn(e01, w[((4 * g + r) % kWin) / 2], acc[r]);          // taps 4g+0,1 x W[r],W[r+1]
+#pragma unroll
+      for (int r = 0; r < kR; r += 2) acc[r] = __ffma2_rn(e23, w[((4 * g + r + 2) % kWin) / 2], acc[r]);      // taps 4g+2,3 x W[r+2],W[r+3]
+#pragma unroll
+      for (int r = 0; r < kR; r += 2) acc[r + 1] = __ffma2_rn(o01, w[((4 * g + r) % kWin) / 2], acc[r + 1]);  // odd outputs: shifted taps,
+#pragma unroll
+      for (int r = 0; r < kR; r += 2) acc[r + 1] = __ffma2_rn(o23, w[((4 * g + r + 2) % kWin) / 2], acc[r + 1]);  // same window pairs
+    }
+  }
+  if (glast > 0) {
+#pragma unroll
+    for (int g = 0; g < kGroups - 1; ++g) {
+      if (g >= glast) break;
       // the chunk that completes the window of this group lands in the slot freed by the previous group
 #ifdef RB_WIN_LDS64
       w[((kR + 4 * g) % kWin) / 2] = lds64(xq);
@@ -189,7 +223,8 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
         __syncthreads();
       }
       const int z = e & 3;                                      // leading zero taps that align the window to 16 B
-      const int nbody = (z + kseg + 1 + kBodyTaps - 1) / kBodyTaps;
+      const int ngroups = (z + kseg + 1 + 3) >> 2;              // 4-tap groups holding taps (+1: the odd-output copy is shifted)
+      const int nbody = (ngroups + kBodyTaps / 4 - 1) / (kBodyTaps / 4);
       for (int i = tid; i < nbody * kBodyTaps; i += kThreads) {
         const int m = i - z;                                    // he[i] = h[i0 + m]
         const float hv = (m >= 0 && m < kseg) ? __ldg(taps + t0 + (K - 1 - (i0 + m))) : 0.f;
@@ -206,7 +241,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
         src = sm.xp;
       }
       __syncthreads();
-      if (warp_active) conv_segment(acc, src, sm.he, sm.ho, e - z, nbody);
+      if (warp_active) conv_segment(acc, src, sm.he, sm.ho, e - z, ngroups);
     }
   }
   __syncthreads();  // everyone is done reading xp; reuse it to transpose the outputs
