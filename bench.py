@@ -178,6 +178,17 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def traffic_for(kernel, algo, batch):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    ``ncu --set full`` capture of the same configuration (profiles/traffic.json), or None when there is none."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        table = json.load(f)
+    return table.get(f"{kernel}:algo{algo}:b{batch}")
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -393,6 +404,22 @@ def gpu_arm(a):
         fir_avg_ms = fir_ms.value / max(1, fir_n.value)
         fir_per_step = fir_n.value / a.steps
         achieved_tf = flops_step / max(1e-9, fir_avg_ms * fir_per_step * 1e-3) / 1e12 if fir_n.value else None
+        step_s = total_ms / a.steps * 1e-3
+        step_hbm = {"bound": "hbm", "achieved": bytes_step / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": bytes_step / step_s / 1e9 / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes_per_step": bytes_step}
+        if fir_n.value:  # FP32-pipe bound: the FIR-bank kernel (with its fused per-utterance tail) is the step
+            roofline = {
+                "bound": "fp32", "kernel": "fir_bank_kernel", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp32_peak, "traffic": traffic_for("fir_bank_kernel", algo, B),
+                "peak_source": "FFMA2 register-resident chain measured in this run (rb_probe_fp32); scalar FFMA chain gave %.1f; "
+                               "MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only and north_star puts this path on the "
+                               "non-tensor FP32 pipe" % fp32_ffma,
+                "kernel_ms_per_launch": fir_avg_ms, "kernel_launches_per_step": fir_per_step,
+                "kernel_share_of_step": (fir_avg_ms * fir_per_step) / (total_ms / a.steps),
+                "algorithmic_flops_per_step": flops_step, "step_hbm": step_hbm}
+        else:           # HBM bound (algo 2): one fused kernel per step, algorithmic bytes over the step time
+            roofline = dict(step_hbm, kernel="isd_fused_kernel", traffic=traffic_for("isd_fused_kernel", algo, B),
+                            kernel_ms_per_launch=total_ms / a.steps, kernel_launches_per_step=1.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -402,17 +429,7 @@ def gpu_arm(a):
                        "l2": "inputs (%.2f GB per GPU) larger than L2; no explicit flush" % (x.numel() * 4 / 1e9),
                        "plan_bank": "drawn on the host (%s planner, reference RNG stream order), resident in HBM before timing" % ("numpy" if a.planner == "numpy" else "native"),
                        "step_ms_min_max": [min(step_ms), max(step_ms)], "plan_draw_s_setup": t_plan, "host_plan_workers": workers},
-            "roofline": {
-                "bound": "fp32", "kernel": "fir_bank_kernel", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                "frac": (achieved_tf / fp32_peak) if achieved_tf else None, "traffic": None,
-                "peak_source": "FFMA2 register-resident chain measured in this run (rb_probe_fp32); scalar FFMA chain gave %.1f" % fp32_ffma,
-                "kernel_ms_per_launch": fir_avg_ms, "kernel_launches_per_step": fir_per_step,
-                "kernel_share_of_step": (fir_avg_ms * fir_per_step) / (total_ms / a.steps),
-                "algorithmic_flops_per_step": flops_step,
-                "step_hbm": {"bound": "hbm", "achieved": bytes_step / (total_ms / a.steps * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": bytes_step / (total_ms / a.steps * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
-                             "algorithmic_bytes_per_step": bytes_step},
-            },
+            "roofline": roofline,
             "e2e": {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "includes": ("H2D of waveforms + seeds, plan draw ON THE DEVICE (bit-exact replay of numpy's MT19937 stream, "
                                  "rb_devplan_draw), kernels, D2H; chunked 3-stage pipeline through rb_process_host_seeded"

@@ -58,6 +58,7 @@ struct Workspace {
   float* stats_a;
   float* stats_b;
   UttParams* params;
+  uint32_t* counters;  // per-utterance tile arrival counters of the fused FIR tail
   uint32_t* mask;
   int mask_ld;
   float* buf0;  // raw FIR-bank output / coloured noise
@@ -79,6 +80,7 @@ Workspace carve(void* base, int B, int ld) {
   w.stats_a = (float*)take((size_t)B * ntiles * kStatN * sizeof(float));
   w.stats_b = (float*)take((size_t)B * ntiles * kStatN * sizeof(float));
   w.params = (UttParams*)take((size_t)B * sizeof(UttParams));
+  w.counters = (uint32_t*)take((size_t)B * sizeof(uint32_t));
   w.mask_ld = mask_ld_for(ld);
   w.mask = (uint32_t*)take((size_t)B * w.mask_ld * sizeof(uint32_t));
   w.buf0 = (float*)take((size_t)B * ld * sizeof(float));
@@ -110,37 +112,34 @@ int check_ws(void* ws, size_t ws_bytes, int B, int ld, Workspace* out) {
     if (rc__ != RB_OK) return rc__; \
   } while (0)
 
-// LnL (optionally followed by ISD in the same finalise / apply passes): x -> out
+// LnL (optionally followed by ISD): x -> out. One FIR-bank launch; its fused tail does mean removal, normWav, the impulse
+// scatter and the second normWav per utterance.
 int do_lnl(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl, bool with_isd, float* out, const Workspace& w,
            cudaStream_t st) {
   if (!pl || pl->n_f < 1 || !pl->lnl_taps || !pl->lnl_tap_off) return RB_ERR_PLAN;
   if (with_isd && (!pl->isd_off || !pl->isd_idx || !pl->isd_fr)) return RB_ERR_PLAN;
   if (with_isd) RB_TRY(launch_mask_build(pl->isd_off, pl->isd_idx, len, B, w.mask, w.mask_ld, st));
-  RB_TRY(launch_fir_bank(x, len, B, ld, pl->lnl_taps, pl->lnl_tap_off, pl->n_f, 1, 1, w.buf0, w.stats_a,
-                         with_isd ? w.mask : nullptr, w.mask_ld, st));
-  FinalizeArgs fa{};
-  fa.stats = w.stats_a;
-  fa.ntiles = tiles_for(ld);
-  fa.len = len;
-  fa.center = 1;
-  fa.always = 0;
-  fa.raw = w.buf0;
-  fa.ld = ld;
-  fa.isd_off = with_isd ? pl->isd_off : nullptr;
-  fa.isd_idx = pl->isd_idx;
-  fa.isd_fr = pl->isd_fr;
-  fa.g_sd = pl->g_sd;
-  fa.out = w.params;
-  RB_TRY(launch_finalize(fa, B, st));
-  RB_TRY(launch_apply_affine(w.buf0, len, B, ld, w.params, out, st));
-  if (with_isd)
-    RB_TRY(launch_isd_scatter(w.buf0, len, B, ld, pl->isd_off, pl->isd_idx, pl->isd_fr, pl->g_sd, w.params, out, st));
-  return RB_OK;
+  FirTail tail;
+  tail.mode = TAIL_AFFINE;
+  tail.counters = w.counters;
+  tail.out = out;
+  if (with_isd) {
+    tail.isd_off = pl->isd_off;
+    tail.isd_idx = pl->isd_idx;
+    tail.isd_fr = pl->isd_fr;
+    tail.g_sd = pl->g_sd;
+  }
+  return launch_fir_bank(x, len, B, ld, pl->lnl_taps, pl->lnl_tap_off, pl->n_f, 1, 1, w.buf0, w.stats_a,
+                         with_isd ? w.mask : nullptr, w.mask_ld, tail, st);
 }
 
 // ISD on an existing waveform: x -> out (out != x)
 int do_isd(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl, float* out, const Workspace& w, cudaStream_t st) {
   if (!pl || !pl->isd_off || !pl->isd_idx || !pl->isd_fr) return RB_ERR_PLAN;
+  {  // one kernel, one pass over HBM; the multi-pass composition below only serves utterances whose mask exceeds shared memory
+    const int rc = launch_isd_fused(x, len, B, ld, 0, pl->isd_off, pl->isd_idx, pl->isd_fr, pl->g_sd, out, st);
+    if (rc != RB_ERR_UNSUPPORTED) return rc;
+  }
   RB_TRY(launch_mask_build(pl->isd_off, pl->isd_idx, len, B, w.mask, w.mask_ld, st));
   RB_TRY(launch_dense_stats(x, len, B, ld, w.stats_a, w.mask, w.mask_ld, st));
   FinalizeArgs fa{};
@@ -160,31 +159,24 @@ int do_isd(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
   return RB_OK;
 }
 
-// SSI: x -> out (out may alias x). Uses buf0 for the coloured noise.
+// SSI: x -> out (out must not alias x: the tail of one utterance reads x while other tiles still compute statistics of it).
+// One FIR-bank launch on the noise; its fused tail takes both norms and adds the scaled coloured noise. buf0 = coloured noise.
 int do_ssi(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl, float* out, const Workspace& w, cudaStream_t st) {
   if (!pl || !pl->ssi_noise || !pl->ssi_taps || !pl->ssi_tap_off || !pl->ssi_snr_db) return RB_ERR_PLAN;
   if ((uintptr_t)pl->ssi_noise & 15u) return RB_ERR_ALIGNMENT;
-  RB_TRY(launch_fir_bank(pl->ssi_noise, len, B, ld, pl->ssi_taps, pl->ssi_tap_off, 1, 1, 0, w.buf0, w.stats_a, nullptr, 0, st));
-  RB_TRY(launch_dense_stats(x, len, B, ld, w.stats_b, nullptr, 0, st));
-  RB_TRY(launch_ssi_finalize(w.stats_b, w.stats_a, tiles_for(ld), pl->ssi_snr_db, w.params, B, st));
-  RB_TRY(launch_apply_ssi(x, w.buf0, len, B, ld, w.params, out, st));
-  return RB_OK;
+  FirTail tail;
+  tail.mode = TAIL_SSI;
+  tail.counters = w.counters;
+  tail.out = out;
+  tail.aux = x;
+  tail.snr_db = pl->ssi_snr_db;
+  return launch_fir_bank(pl->ssi_noise, len, B, ld, pl->ssi_taps, pl->ssi_tap_off, 1, 1, 0, w.buf0, w.stats_a, nullptr, 0, tail, st);
 }
 
 // normWav: x -> out
 int do_normwav(const float* x, const int32_t* len, int B, int ld, int always, float* out, const Workspace& w, cudaStream_t st) {
-  RB_TRY(launch_dense_stats(x, len, B, ld, w.stats_a, nullptr, 0, st));
-  FinalizeArgs fa{};
-  fa.stats = w.stats_a;
-  fa.ntiles = tiles_for(ld);
-  fa.len = len;
-  fa.always = always ? 1 : 0;
-  fa.raw = x;
-  fa.ld = ld;
-  fa.out = w.params;
-  RB_TRY(launch_finalize(fa, B, st));
-  RB_TRY(launch_apply_affine(x, len, B, ld, w.params, out, st));
-  return RB_OK;
+  (void)w;
+  return launch_isd_fused(x, len, B, ld, always, nullptr, nullptr, nullptr, 0.f, out, st);
 }
 
 }  // namespace
@@ -248,7 +240,7 @@ int rb_filter_fir(const float* x, const int32_t* len, int B, int ld, const float
   RB_TRY(check_batch(x, len, B, ld, y));
   if (B == 0 || ld == 0) return RB_OK;
   if (!taps || !tap_off) return RB_ERR_INVALID_ARG;
-  return launch_fir_bank(x, len, B, ld, taps, tap_off, 1, 1, 0, y, nullptr, nullptr, 0, (cudaStream_t)stream);
+  return launch_fir_bank(x, len, B, ld, taps, tap_off, 1, 1, 0, y, nullptr, nullptr, 0, FirTail(), (cudaStream_t)stream);
 }
 
 int rb_normwav(const float* x, const int32_t* len, int B, int ld, int always, float* y, void* workspace, size_t workspace_bytes,

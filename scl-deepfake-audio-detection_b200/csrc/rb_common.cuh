@@ -26,7 +26,7 @@ constexpr int kMaxReach = kXS - (kThreads - 1) * kR - kWin - kBodyTaps;  // e + 
 // ---- per-tile partial statistics written by the FIR-bank and dense-stats kernels --------------------
 // [B][ntiles][kStatN] floats: sum, sum of squares, min, max, min/max over samples NOT hit by an ISD impulse.
 constexpr int kStatN = 8;
-enum { S_SUM = 0, S_SUMSQ = 1, S_MIN = 2, S_MAX = 3, S_MINU = 4, S_MAXU = 5 };
+enum { S_SUM = 0, S_SUMSQ = 1, S_MIN = 2, S_MAX = 3, S_MINU = 4, S_MAXU = 5, S_AUXSQ = 6 };  // AUXSQ: sum of squares of FirTail::aux
 
 // ---- per-utterance scalars consumed by the dense apply pass: out = ((in - sub) / div1) / div2 -------
 struct __align__(16) UttParams {
@@ -85,11 +85,39 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ float nan_max(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
 __device__ __forceinline__ float nan_min(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
 
+// ---- fused tail of the FIR-bank kernel ---------------------------------------------------------------------------------
+// The per-utterance reductions (mean, peak, norms) need every tile of the utterance. Instead of separate finalise / apply
+// passes, the CTA that completes an utterance's last tile (a per-utterance arrival counter) finalises it in place:
+//   TAIL_AFFINE  out = normWav(y - mean(y), 0), optionally followed by the ISD scatter and its normWav (LnL, LnL -> ISD)
+//   TAIL_SSI     out = aux + y * ||aux|| / (||y|| * 10^(snr/20))                                        (SSI)
+enum { TAIL_NONE = 0, TAIL_AFFINE = 1, TAIL_SSI = 2 };
+struct FirTail {
+  int mode = TAIL_NONE;
+  uint32_t* counters = nullptr;      // [B] arrival counters (zeroed by the launcher, left zero by the kernel)
+  float* out = nullptr;              // [B][ld] final waveform
+  const int32_t* isd_off = nullptr;  // TAIL_AFFINE: impulses (NULL = none); offsets are absolute into isd_idx / isd_fr
+  const int32_t* isd_idx = nullptr;
+  const double* isd_fr = nullptr;
+  float g_sd = 0.f;
+  const float* aux = nullptr;        // TAIL_SSI: the signal the noise is added to, [B][ld]
+  const float* snr_db = nullptr;     // TAIL_SSI: [B]
+  // the same tail for the sub-batch starting at utterance b0
+  FirTail shifted(int b0, int ld) const {
+    FirTail t = *this;
+    if (t.counters) t.counters += b0;
+    if (t.out) t.out += (size_t)b0 * ld;
+    if (t.isd_off) t.isd_off += b0;
+    if (t.aux) t.aux += (size_t)b0 * ld;
+    if (t.snr_db) t.snr_db += b0;
+    return t;
+  }
+};
+
 // ---- kernel launchers shared between translation units (all asynchronous on `st`) ------------------
-// FIR bank: y[u] = sum_f FIR(x[u] ** (pow_base + f*pow_step), taps of filter (u,f)); optional tile stats + ISD mask.
+// FIR bank: y[u] = sum_f FIR(x[u] ** (pow_base + f*pow_step), taps of filter (u,f)); optional tile stats + ISD mask + tail.
 int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const float* taps, const int32_t* tap_off,
                     int n_f, int pow_base, int pow_step, float* y, float* stats /*nullable*/,
-                    const uint32_t* mask /*nullable*/, int mask_ld, cudaStream_t st);
+                    const uint32_t* mask /*nullable*/, int mask_ld, const FirTail& tail, cudaStream_t st);
 
 // Device-side planner, stage by stage (rb_devplan.cu); rb_devplan_draw runs all four for the whole batch. The pipelined host
 // entry interleaves stages 2/3 of one chunk with the kernels of the previous chunk.

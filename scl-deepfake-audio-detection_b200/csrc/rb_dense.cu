@@ -6,6 +6,7 @@
 //   normWav 20-25, LnL tail (mean removal + normWav) 67-68, ISD 76-84, SSI tail 93-96.
 #include "rb_common.cuh"
 #include "rb_dense.cuh"
+#include "rb_finalize.cuh"
 
 namespace rb {
 
@@ -99,112 +100,31 @@ dense_stats_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_
   }
 }
 
-// The impulsive-noise value at one position, with the reference's exact operation order and precisions
-// (RawBoost.py:81-82 on float32 input): t = fl32(g_sd*x), r = fl64(t*f_r), y = fl32(fl64(x + r)).
-__device__ __forceinline__ float isd_value(float v, float g_sd, double fr) {
-  const float t = __fmul_rn(g_sd, v);
-  const double r = __dmul_rn((double)t, fr);
-  return (float)__dadd_rn((double)v, r);
-}
-
-// ---- per-utterance finaliser: one CTA per utterance ----------------------------------------------
+// ---- per-utterance finaliser: one CTA per utterance (arithmetic in rb_finalize.cuh) ----------------------------------------
 __global__ void __launch_bounds__(kThreads)
 finalize_kernel(FinalizeArgs a) {
-  __shared__ double red_sum[4];
-  __shared__ float red_f[4][4];
-  __shared__ float bc[4];
-  const int u = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u = blockIdx.x;
   const int n = a.len[u];
-  const float* st = a.stats + (size_t)u * a.ntiles * kStatN;
-  double sum = 0.0;
-  float mn = INFINITY, mx = -INFINITY, mnu = INFINITY, mxu = -INFINITY;
-  for (int t = tid; t < a.ntiles; t += kThreads) {
-    sum += (double)st[t * kStatN + S_SUM];
-    mn = fminf(mn, st[t * kStatN + S_MIN]);
-    mx = fmaxf(mx, st[t * kStatN + S_MAX]);
-    mnu = fminf(mnu, st[t * kStatN + S_MINU]);
-    mxu = fmaxf(mxu, st[t * kStatN + S_MAXU]);
-  }
-  sum = warp_sum(sum);
-  mn = warp_min(mn);
-  mx = warp_max(mx);
-  mnu = warp_min(mnu);
-  mxu = warp_max(mxu);
-  if (lane == 0) {
-    red_sum[warp] = sum;
-    red_f[warp][0] = mn;
-    red_f[warp][1] = mx;
-    red_f[warp][2] = mnu;
-    red_f[warp][3] = mxu;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const double s = (red_sum[0] + red_sum[1]) + (red_sum[2] + red_sum[3]);
-    const float fmn = fminf(fminf(red_f[0][0], red_f[1][0]), fminf(red_f[2][0], red_f[3][0]));
-    const float fmx = fmaxf(fmaxf(red_f[0][1], red_f[1][1]), fmaxf(red_f[2][1], red_f[3][1]));
-    const float fmnu = fminf(fminf(red_f[0][2], red_f[1][2]), fminf(red_f[2][2], red_f[3][2]));
-    const float fmxu = fmaxf(fmaxf(red_f[0][3], red_f[1][3]), fmaxf(red_f[2][3], red_f[3][3]));
-    const float sub = (a.center && n > 0) ? (float)(s / (double)n) : 0.f;
-    float m1 = (n > 0) ? fmaxf(fabsf(fmx - sub), fabsf(fmn - sub)) : 0.f;
-    const float div1 = (n > 0 && (a.always || m1 > 1.f)) ? m1 : 1.f;
-    // peak of the untouched samples after the first normalisation (fp32 division is monotone, so the peak of
-    // the quotients is the quotient of the peak)
-    float mu = 0.f;
-    if (fmnu <= fmxu) mu = fmaxf(fabsf(fmxu - sub), fabsf(fmnu - sub)) / div1;
-    bc[0] = sub;
-    bc[1] = div1;
-    bc[2] = mu;
-  }
-  __syncthreads();
-  const float sub = bc[0], div1 = bc[1];
-  float div2 = 1.f;
-  if (a.isd_off) {
-    const float* row = a.raw + (size_t)u * a.ld;
-    float mt = 0.f;
-    for (int i = a.isd_off[u] + tid; i < a.isd_off[u + 1]; i += kThreads) {
-      const int p = a.isd_idx[i];
-      if (p >= 0 && p < n) {
-        const float v = (row[p] - sub) / div1;
-        mt = fmaxf(mt, fabsf(isd_value(v, a.g_sd, a.isd_fr[i])));
-      }
-    }
-    mt = warp_max(mt);
-    __syncthreads();
-    if (lane == 0) red_f[warp][0] = mt;
-    __syncthreads();
-    if (tid == 0) {
-      const float m2 = fmaxf(bc[2], fmaxf(fmaxf(red_f[0][0], red_f[1][0]), fmaxf(red_f[2][0], red_f[3][0])));
-      div2 = (m2 > 1.f) ? m2 : 1.f;
-    }
-  }
-  if (tid == 0) {
-    UttParams p;
-    p.sub = sub;
-    p.div1 = div1;
-    p.div2 = div2;
-    p.scale = 0.f;
-    a.out[u] = p;
-  }
+  const bool with_isd = a.isd_off != nullptr;
+  const UttParams p = finalize_block(a.stats + (size_t)u * a.ntiles * kStatN, a.ntiles, n, a.center, a.always,
+                                     a.raw + (size_t)u * a.ld, a.isd_idx, a.isd_fr, with_isd ? a.isd_off[u] : 0,
+                                     with_isd ? a.isd_off[u + 1] : 0, with_isd, a.g_sd);
+  if (threadIdx.x == 0) a.out[u] = p;
 }
 
-// ---- SSI scale: ||x||_2 / (||coloured noise||_2 * 10^(snr/20))  (RawBoost.py:95) ------------------
+// ---- SSI scale (RawBoost.py:95) -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
 ssi_finalize_kernel(const float* __restrict__ stats_x, const float* __restrict__ stats_n, int ntiles,
                     const float* __restrict__ snr_db, UttParams* __restrict__ out) {
-  const int u = blockIdx.x, lane = threadIdx.x;
-  double sx = 0.0, sn = 0.0;
-  for (int t = lane; t < ntiles; t += 32) {
-    sx += (double)stats_x[((size_t)u * ntiles + t) * kStatN + S_SUMSQ];
-    sn += (double)stats_n[((size_t)u * ntiles + t) * kStatN + S_SUMSQ];
-  }
-  sx = warp_sum(sx);
-  sn = warp_sum(sn);
-  if (lane == 0) {
+  const int u = blockIdx.x;
+  const float scale = ssi_scale_block(stats_x + (size_t)u * ntiles * kStatN, S_SUMSQ, stats_n + (size_t)u * ntiles * kStatN, ntiles,
+                                      snr_db[u]);
+  if (threadIdx.x == 0) {
     UttParams p;
     p.sub = 0.f;
     p.div1 = 1.f;
     p.div2 = 1.f;
-    p.scale = (float)(sqrt(sx) / (sqrt(sn) * pow(10.0, 0.05 * (double)snr_db[u])));
+    p.scale = scale;
     out[u] = p;
   }
 }
@@ -251,7 +171,7 @@ apply_kernel(const float* __restrict__ a, const float* __restrict__ b, const int
     float r[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (MODE == APPLY_AFFINE) r[q] = __fdiv_rn(__fdiv_rn(__fsub_rn(ea[q], pr.sub), pr.div1), pr.div2);
+      if (MODE == APPLY_AFFINE) r[q] = affine_value(ea[q], pr);
       else if (MODE == APPLY_SSI) r[q] = __fmaf_rn(eb[q], pr.scale, ea[q]);
       else r[q] = __fadd_rn(ea[q], eb[q]);
     }
@@ -279,6 +199,160 @@ isd_scatter_kernel(const float* __restrict__ raw, const int32_t* __restrict__ le
     if (p >= 0 && p < len) {
       const float v = __fdiv_rn(__fsub_rn(row[p], pr.sub), pr.div1);
       ro[p] = __fdiv_rn(isd_value(v, g_sd, isd_fr[i]), pr.div2);
+    }
+  }
+}
+
+// ---- ISD / normWav in ONE pass over HBM: one CTA per utterance -----------------------------------------------------------
+// normWav(x, always) followed (optionally) by the impulse scatter and its normWav(., 0) (RawBoost.py:20-25, 76-84). Every
+// quantity is a max / min, so the result does not depend on the reduction order and equals the multi-pass path bit for bit.
+// The waveform is read from HBM once (statistics), read again while still L2-resident (apply) and written once; the impulse
+// bit mask lives in shared memory.
+constexpr int kFusedThreads = 512;
+
+__global__ void __launch_bounds__(kFusedThreads)
+isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, int always,
+                 const int32_t* __restrict__ isd_off, const int32_t* __restrict__ isd_idx, const double* __restrict__ isd_fr,
+                 float g_sd, float* __restrict__ out) {
+  extern __shared__ uint32_t smask[];  // [ceil(len/32)] impulse bit mask (unused without impulses)
+  __shared__ float red[kFusedThreads / 32][2];
+  __shared__ float bc[3];
+  const int u = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int len = len_arr[u];
+  if (len <= 0) return;
+  const float* row = x + (size_t)u * ld;
+  float* orow = out + (size_t)u * ld;
+  const bool with_isd = isd_off != nullptr;
+  const int ibeg = with_isd ? isd_off[u] : 0, iend = with_isd ? isd_off[u + 1] : 0;
+  const int nwords = (len + 31) >> 5;
+  if (with_isd) {
+    for (int w = tid; w < nwords; w += kFusedThreads) smask[w] = 0u;
+    __syncthreads();
+    for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
+      const int p = isd_idx[i];
+      if (p >= 0 && p < len) atomicOr(smask + (p >> 5), 1u << (p & 31));
+    }
+    __syncthreads();
+  }
+  // pass 1: peak over all samples and over the samples no impulse touches (NaN-propagating like numpy's amax)
+  const int nchunk = (len + 3) >> 2;
+  float m_all = 0.f, m_unt = 0.f;
+  bool nan_all = false, nan_unt = false;
+  constexpr int kU = 8;  // float4 loads in flight per thread: the pass is latency-bound otherwise
+  for (int c0 = tid; c0 < nchunk; c0 += kU * kFusedThreads) {
+    float4 v[kU];
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      const int p = 4 * (c0 + k * kFusedThreads);
+      if (p + 3 < len) {
+        v[k] = __ldg(reinterpret_cast<const float4*>(row + p));
+      } else {
+        v[k].x = (p + 0 < len) ? __ldg(row + p + 0) : 0.f;
+        v[k].y = (p + 1 < len) ? __ldg(row + p + 1) : 0.f;
+        v[k].z = (p + 2 < len) ? __ldg(row + p + 2) : 0.f;
+        v[k].w = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      const int p = 4 * (c0 + k * kFusedThreads);
+      const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      const uint32_t hit = (with_isd && p < len) ? ((smask[p >> 5] >> (p & 31)) & 0xFu) : 0u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float a = fabsf(e[q]);  // padding lanes hold 0: neutral for a peak
+        nan_all |= (a != a);
+        m_all = fmaxf(m_all, a);
+        if (!((hit >> q) & 1u)) {
+          nan_unt |= (a != a);
+          m_unt = fmaxf(m_unt, a);
+        }
+      }
+    }
+  }
+  if (nan_all) m_all = NAN;
+  if (nan_unt) m_unt = NAN;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m_all = nan_max(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
+    m_unt = nan_max(m_unt, __shfl_xor_sync(0xffffffffu, m_unt, o));
+  }
+  if (lane == 0) {
+    red[warp][0] = m_all;
+    red[warp][1] = m_unt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float a = red[0][0], b = red[0][1];
+    for (int w = 1; w < kFusedThreads / 32; ++w) {
+      a = nan_max(a, red[w][0]);
+      b = nan_max(b, red[w][1]);
+    }
+    const float div1 = (always || a > 1.f) ? a : 1.f;  // a NaN peak: "NaN > 1" is false, like the reference
+    bc[0] = div1;
+    bc[1] = b / div1;  // peak of the untouched samples after the first normalisation
+  }
+  __syncthreads();
+  const float div1 = bc[0];
+  float div2 = 1.f;
+  if (with_isd) {
+    float mt = 0.f;
+    for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
+      const int p = isd_idx[i];
+      if (p >= 0 && p < len) mt = fmaxf(mt, fabsf(isd_value(__fdiv_rn(__ldg(row + p), div1), g_sd, isd_fr[i])));
+    }
+    mt = warp_max(mt);
+    __syncthreads();
+    if (lane == 0) red[warp][0] = mt;
+    __syncthreads();
+    if (tid == 0) {
+      float m2 = bc[1];
+      for (int w = 0; w < kFusedThreads / 32; ++w) m2 = fmaxf(m2, red[w][0]);
+      bc[2] = (m2 > 1.f) ? m2 : 1.f;
+    }
+    __syncthreads();
+    div2 = bc[2];
+  }
+  // pass 2: out = (x / div1) / div2 (division by 1 skipped: identity), then the impulses
+  const int ndiv = (div1 != 1.f) + (div2 != 1.f);
+  const float dv = (div1 != 1.f) ? div1 : div2;
+  auto nrm = [&](float e) {
+    if (ndiv == 0) return e;
+    if (ndiv == 1) return __fdiv_rn(e, dv);
+    return __fdiv_rn(__fdiv_rn(e, div1), div2);
+  };
+  for (int c0 = tid; c0 < nchunk; c0 += kU * kFusedThreads) {
+    float4 v[kU];
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      const int p = 4 * (c0 + k * kFusedThreads);
+      if (p + 3 < len) {
+        v[k] = __ldg(reinterpret_cast<const float4*>(row + p));
+      } else {
+        v[k].x = (p + 0 < len) ? __ldg(row + p + 0) : 0.f;
+        v[k].y = (p + 1 < len) ? __ldg(row + p + 1) : 0.f;
+        v[k].z = (p + 2 < len) ? __ldg(row + p + 2) : 0.f;
+        v[k].w = 0.f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      const int p = 4 * (c0 + k * kFusedThreads);
+      const float4 r = make_float4(nrm(v[k].x), nrm(v[k].y), nrm(v[k].z), nrm(v[k].w));
+      if (p + 3 < len) {
+        *reinterpret_cast<float4*>(orow + p) = r;
+      } else {
+        if (p + 0 < len) orow[p + 0] = r.x;
+        if (p + 1 < len) orow[p + 1] = r.y;
+        if (p + 2 < len) orow[p + 2] = r.z;
+      }
+    }
+  }
+  if (with_isd) {
+    __syncthreads();  // impulse positions overwrite what the dense pass just stored
+    for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
+      const int p = isd_idx[i];
+      if (p >= 0 && p < len) orow[p] = __fdiv_rn(isd_value(__fdiv_rn(__ldg(row + p), div1), g_sd, isd_fr[i]), div2);
     }
   }
 }
@@ -362,4 +436,19 @@ int launch_isd_scatter(const float* raw, const int32_t* len, int B, int ld, cons
   return RB_OK;
 }
 
+}  // namespace rb
+
+namespace rb {
+// normWav(x, always) [+ ISD] in one kernel. Returns RB_ERR_UNSUPPORTED when the impulse mask does not fit shared memory
+// (utterances beyond ~1.8 M samples); the caller then takes the multi-pass path.
+int launch_isd_fused(const float* x, const int32_t* len, int B, int ld, int always, const int32_t* isd_off, const int32_t* isd_idx,
+                     const double* isd_fr, float g_sd, float* out, cudaStream_t st) {
+  if (B <= 0) return RB_OK;
+  const size_t smem = isd_off ? ((size_t)(ld + 31) / 32) * 4 : 0;
+  if (smem > 200 * 1024) return RB_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(isd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  isd_fused_kernel<<<B, kFusedThreads, smem, st>>>(x, len, ld, always, isd_off, isd_idx, isd_fr, g_sd, out);
+  RB_LAUNCH_CHECK();
+  return RB_OK;
+}
 }  // namespace rb

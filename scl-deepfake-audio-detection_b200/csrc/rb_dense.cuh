@@ -34,4 +34,7 @@ int launch_apply_sum(const float* a, const float* b, const int32_t* len, int B, 
 int launch_isd_scatter(const float* raw, const int32_t* len, int B, int ld, const int32_t* isd_off, const int32_t* isd_idx,
                        const double* isd_fr, float g_sd, const UttParams* params, float* out, cudaStream_t st);
 
+int launch_isd_fused(const float* x, const int32_t* len, int B, int ld, int always, const int32_t* isd_off, const int32_t* isd_idx,
+                     const double* isd_fr, float g_sd, float* out, cudaStream_t st);
+
 }  // namespace rb

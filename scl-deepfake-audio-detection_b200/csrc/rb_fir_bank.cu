@@ -28,6 +28,7 @@
 //    from a per-utterance bit mask) via warp shuffles; outputs go through shared memory so the global store is
 //    a coalesced STG.128 stream.
 #include "rb_common.cuh"
+#include "rb_finalize.cuh"
 
 namespace rb {
 
@@ -171,8 +172,9 @@ __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __r
 __global__ void __launch_bounds__(kThreads, RB_MIN_BLOCKS)
 fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, const float* __restrict__ taps,
                 const int32_t* __restrict__ tap_off, int n_f, int pow_base, int pow_step, float* __restrict__ y,
-                float* __restrict__ stats, const uint32_t* __restrict__ mask, int mask_ld) {
+                float* __restrict__ stats, const uint32_t* __restrict__ mask, int mask_ld, FirTail tail) {
   __shared__ FirSmem sm;
+  __shared__ int s_last;
   const int u = blockIdx.y;
   const int tile = blockIdx.x;
   const int ntiles = gridDim.x;
@@ -315,14 +317,153 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
         if (p + q < valid) yrow[p + q] = sm.xp[p + q];
     }
   }
+  if (tail.mode == TAIL_NONE) return;
+
+  // ---- fused tail: the CTA that finishes the last tile of an utterance finalises the whole utterance -----------------------
+  // (per-utterance reductions need every tile, so this is the one grid-level dependency of the path; the raw tiles were
+  // written a moment ago and are read back from L2 while the other CTAs of the SM keep the FP32 pipe busy.)
+  if (tail.mode == TAIL_SSI) {  // per-tile sum of squares of the signal the noise is added to
+    const float* arow = tail.aux + (size_t)u * ld + tile0;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kR / 4; ++k) {
+      const int p = 4 * (k * kThreads + tid);
+      if (p + 3 < valid) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(arow + p));
+        sq = fmaf(v.x, v.x, sq);
+        sq = fmaf(v.y, v.y, sq);
+        sq = fmaf(v.z, v.z, sq);
+        sq = fmaf(v.w, v.w, sq);
+      } else {
+        for (int q = 0; q < 4; ++q)
+          if (p + q < valid) {
+            const float e = __ldg(arow + p + q);
+            sq = fmaf(e, e, sq);
+          }
+      }
+    }
+    sq = warp_sum(sq);
+    __syncthreads();  // sm.red was read by the statistics above
+    if (lane == 0) sm.red[warp][0] = sq;
+    __syncthreads();
+    if (tid == 0) st_out[S_AUXSQ] = (sm.red[0][0] + sm.red[1][0]) + (sm.red[2][0] + sm.red[3][0]);
+  }
+  const int nact = (len + kTile - 1) / kTile;  // tiles of this utterance that do work (the others returned at once)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned prev = atomicAdd(tail.counters + u, 1u);
+    s_last = (prev == (unsigned)(nact - 1));
+    if (s_last) tail.counters[u] = 0u;  // ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* raw = y + (size_t)u * ld;
+  float* orow = tail.out + (size_t)u * ld;
+  const float* ust = stats + (size_t)u * ntiles * kStatN;
+  const int nchunk = (len + 3) >> 2;
+  if (tail.mode == TAIL_AFFINE) {
+    const bool with_isd = tail.isd_off != nullptr;
+    const int ibeg = with_isd ? tail.isd_off[u] : 0, iend = with_isd ? tail.isd_off[u + 1] : 0;
+    const UttParams pr = finalize_block(ust, nact, len, 1, 0, raw, tail.isd_idx, tail.isd_fr, ibeg, iend, with_isd, tail.g_sd);
+    // division by 1 is the identity: skip the idle normalisations (the common case at speech level), bit for bit the same
+    const int ndiv = (pr.div1 != 1.f) + (pr.div2 != 1.f);
+    const float dv = (pr.div1 != 1.f) ? pr.div1 : pr.div2;
+    auto aff = [&](float e) {
+      const float d = __fsub_rn(e, pr.sub);
+      if (ndiv == 0) return d;
+      if (ndiv == 1) return __fdiv_rn(d, dv);
+      return __fdiv_rn(__fdiv_rn(d, pr.div1), pr.div2);
+    };
+    constexpr int kU = 4;  // chunks in flight per thread: the reads come from L2, keep several outstanding
+    for (int c0 = tid; c0 < nchunk; c0 += kU * kThreads) {
+      float4 v[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const int p = 4 * (c0 + k * kThreads);
+        if (p + 3 < len) {
+          v[k] = __ldcg(reinterpret_cast<const float4*>(raw + p));
+        } else {
+          v[k].x = (p + 0 < len) ? __ldcg(raw + p + 0) : 0.f;
+          v[k].y = (p + 1 < len) ? __ldcg(raw + p + 1) : 0.f;
+          v[k].z = (p + 2 < len) ? __ldcg(raw + p + 2) : 0.f;
+          v[k].w = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const int p = 4 * (c0 + k * kThreads);
+        const float4 r = make_float4(aff(v[k].x), aff(v[k].y), aff(v[k].z), aff(v[k].w));
+        if (p + 3 < len) {
+          *reinterpret_cast<float4*>(orow + p) = r;
+        } else {
+          if (p + 0 < len) orow[p + 0] = r.x;
+          if (p + 1 < len) orow[p + 1] = r.y;
+          if (p + 2 < len) orow[p + 2] = r.z;
+        }
+      }
+    }
+    if (with_isd) {
+      __syncthreads();  // impulse positions overwrite what the dense pass just stored
+      for (int i = ibeg + tid; i < iend; i += kThreads) {
+        const int p = tail.isd_idx[i];
+        if (p >= 0 && p < len) {
+          const float v = __fdiv_rn(__fsub_rn(__ldcg(raw + p), pr.sub), pr.div1);
+          orow[p] = __fdiv_rn(isd_value(v, tail.g_sd, tail.isd_fr[i]), pr.div2);
+        }
+      }
+    }
+  } else {  // TAIL_SSI: out = x + coloured noise * scale  (RawBoost.py:95-96)
+    const float scale = ssi_scale_block(ust, S_AUXSQ, ust, nact, tail.snr_db[u]);
+    const float* arow = tail.aux + (size_t)u * ld;
+    constexpr int kU = 4;
+    for (int c0 = tid; c0 < nchunk; c0 += kU * kThreads) {
+      float4 v[kU], a[kU];
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const int p = 4 * (c0 + k * kThreads);
+        if (p + 3 < len) {
+          v[k] = __ldcg(reinterpret_cast<const float4*>(raw + p));
+          a[k] = __ldg(reinterpret_cast<const float4*>(arow + p));
+        } else {
+          v[k].x = (p + 0 < len) ? __ldcg(raw + p + 0) : 0.f;
+          v[k].y = (p + 1 < len) ? __ldcg(raw + p + 1) : 0.f;
+          v[k].z = (p + 2 < len) ? __ldcg(raw + p + 2) : 0.f;
+          v[k].w = 0.f;
+          a[k].x = (p + 0 < len) ? __ldg(arow + p + 0) : 0.f;
+          a[k].y = (p + 1 < len) ? __ldg(arow + p + 1) : 0.f;
+          a[k].z = (p + 2 < len) ? __ldg(arow + p + 2) : 0.f;
+          a[k].w = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kU; ++k) {
+        const int p = 4 * (c0 + k * kThreads);
+        const float4 r = make_float4(__fmaf_rn(v[k].x, scale, a[k].x), __fmaf_rn(v[k].y, scale, a[k].y),
+                                     __fmaf_rn(v[k].z, scale, a[k].z), __fmaf_rn(v[k].w, scale, a[k].w));
+        if (p + 3 < len) {
+          *reinterpret_cast<float4*>(orow + p) = r;
+        } else {
+          if (p + 0 < len) orow[p + 0] = r.x;
+          if (p + 1 < len) orow[p + 1] = r.y;
+          if (p + 2 < len) orow[p + 2] = r.z;
+        }
+      }
+    }
+  }
 }
 
 }  // namespace
 
 int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const float* taps, const int32_t* tap_off,
                     int n_f, int pow_base, int pow_step, float* y, float* stats, const uint32_t* mask, int mask_ld,
-                    cudaStream_t st) {
+                    const FirTail& tail, cudaStream_t st) {
   if (B <= 0 || ld <= 0) return RB_OK;
+  if (tail.mode != TAIL_NONE) {
+    if (!stats || !tail.counters || !tail.out || (tail.mode == TAIL_SSI && (!tail.aux || !tail.snr_db))) return RB_ERR_INVALID_ARG;
+    RB_CUDA(cudaMemsetAsync(tail.counters, 0, (size_t)B * sizeof(uint32_t), st));
+  }
   // gridDim.y is limited to 65535: split very large batches over several launches.
   const int ntiles = tiles_for(ld);
   for (int b0 = 0; b0 < B; b0 += 65535) {
@@ -332,7 +473,7 @@ int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const flo
     fir_bank_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)b0 * ld, len + b0, ld, taps, tap_off + (size_t)b0 * n_f, n_f,
                                                 pow_base, pow_step, y + (size_t)b0 * ld,
                                                 stats ? stats + (size_t)b0 * ntiles * kStatN : nullptr,
-                                                mask ? mask + (size_t)b0 * mask_ld : nullptr, mask_ld);
+                                                mask ? mask + (size_t)b0 * mask_ld : nullptr, mask_ld, tail.shifted(b0, ld));
     profile_end(st);
     RB_LAUNCH_CHECK();
   }
