@@ -191,6 +191,18 @@ RB_API int rb_devplan_draw(const rb_args* args, int algo, int B, int ld, const i
 RB_API int rb_process_host_seeded(rb_ctx* ctx, int algo, const rb_args* args, const float* x, const int32_t* len,
                                   const uint32_t* seeds, int B, int ld, float* y);
 
+/* ---- the step after the path, for the views of an item -----------------------------------
+ * batch_pad_for_multiview (core_scripts/data_io/wav_augmentation.py:209-282) + the view assembly of
+ * Dataset_for.__getitem__ (asvspoof_2019_augall_3.py:133-142) + the [1,length,V] -> [V,length] reshape of main.py:57-60.
+ * G groups (items) of V views each; view v of group g is row g*V+v of `views` ([G*V, ld], len[G*V], device). Every view
+ * is cut / zero-extended / (repeat_pad) tiled to the length of the group's view 0, then one crop of `length` samples
+ * starting at start[g] (device int32[G], drawn by the host: int(np.random.rand()*(len0-length)), 0 without random trim;
+ * ignored when view 0 is shorter than `length`) is taken from all of them; a short view 0 is tiled up to `length` with
+ * repeat_pad and left at its own length without. layout 0: out[G][length][V] (the Dataset's batch_data); layout 1:
+ * out[G][V][length] (what the model consumes). out_len (nullable, device int32[G]) receives the samples written per view. */
+RB_API int rb_multiview_assemble(const float* views, const int32_t* len, int G, int V, int ld, const int32_t* start, int length,
+                                 int repeat_pad, int layout, float* out, int32_t* out_len, void* stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------------------
  * rb_probe_fp32: runs a register-resident FFMA2 (packed=1) or FFMA (packed=0) chain on every SM and
  * returns the achieved FLOP count in *flops; the caller times it with events on `stream`.

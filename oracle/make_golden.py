@@ -180,5 +180,55 @@ def main():
     print(f"wrote {len(arrays)} arrays ({size/1e6:.2f} MB) and {len(meta['cases'])+len(meta['full'])} case records to {OUT}")
 
 
+def main_multiview():
+    """Fixtures for the step right after the path: ``batch_pad_for_multiview``
+    (core_scripts/data_io/wav_augmentation.py:209-282) and the view assembly of ``Dataset_for.__getitem__``
+    (datautils/asvspoof_2019_augall_3.py:103-146), produced by the unmodified reference."""
+    warnings.simplefilter("ignore", DeprecationWarning)
+    rb, loader = import_reference()
+    nii = loader.nii_wav_aug
+    arrays, meta = {}, {"pad": {}, "item": {}}
+    rs = np.random.RandomState(11)
+    # ---- batch_pad_for_multiview: every branch (first view shorter / longer than the target, zero / repeat pad, crop) ----
+    lens_sets = {"firstlong": [333, 150, 200, 90, 1000], "firstshort": [150, 333, 40, 150], "firstequal": [200, 10, 700],
+                 "single": [517]}
+    case = 0
+    for tag, lens in lens_sets.items():
+        views = [rs.standard_normal((n, 1)).astype(np.float32) for n in lens]
+        arrays[f"pad_in_{tag}"] = np.concatenate([v[:, 0] for v in views])
+        for length in (200, 64):
+            for repeat_pad in (False, True):
+                for trim in (False, True):
+                    np.random.seed(1000 + case)
+                    out = nii.batch_pad_for_multiview([v.copy() for v in views], 16000, length, random_trim_nosil=trim,
+                                                      repeat_pad=repeat_pad)
+                    key = f"pad_{tag}_L{length}_r{int(repeat_pad)}_t{int(trim)}"
+                    arrays[key] = np.concatenate(out, axis=1)
+                    meta["pad"][key] = {"lens": lens, "length": length, "repeat_pad": repeat_pad, "trim": trim, "seed": 1000 + case,
+                                        "input": f"pad_in_{tag}", "out_len": int(out[0].shape[0]), "stream": stream_digest()}
+                    case += 1
+    # ---- one Dataset item, RNG order of __getitem__: 3 vocoded RawBoost12, anchor RawBoost12, (choice), crop ----
+    args = make_args(online_aug=True, aug_dir="")
+    for item, (L, trim_len) in enumerate(((16000, 12000), (9000, 12000))):
+        waves = [synth_utterance(100 + 4 * item + k, L + 37 * k, bool(k % 2)) for k in range(4)]  # anchor, 3 vocoded
+        np.random.seed(4242 + item)
+        aug_voc = [loader.RawBoost12(w, args, 16000, audio_path="x") for w in waves[1:]]
+        aug_anchor = loader.RawBoost12(waves[0], args, 16000, audio_path="x")
+        views = [waves[0], aug_anchor] + waves[1:] + aug_voc
+        batch = nii.batch_pad_for_multiview([np.expand_dims(v, 1) for v in views], 16000, trim_len, random_trim_nosil=True,
+                                            repeat_pad=True)
+        batch = np.concatenate(batch, axis=1)
+        arrays[f"item{item}"] = batch.astype(np.float32)
+        meta["item"][f"item{item}"] = {"L": L, "trim": trim_len, "seed": 4242 + item, "first_wave": 100 + 4 * item,
+                                       "shape": list(batch.shape), "stream": stream_digest()}
+    np.savez_compressed(os.path.join(OUT, "multiview_golden.npz"), **arrays)
+    with open(os.path.join(OUT, "multiview_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    print(f"wrote {len(arrays)} multiview arrays to {OUT}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--multiview" in sys.argv:
+        main_multiview()
+    else:
+        main()

@@ -262,6 +262,45 @@ DEFAULT_ARGS = dict(  # /root/reference/main.py:258-298
 )
 
 
+# --------------------------------------------------------------------------------------------------------
+# the step right after the path: length unification + one shared crop over the views of an item
+# (/root/reference/core_scripts/data_io/wav_augmentation.py:209-282), restated as an index map
+# --------------------------------------------------------------------------------------------------------
+def multiview_crop_plan(first_len, length, random_trim_nosil, repeat_pad):
+    """(start, out_len, wrap) of ``batch_pad_for_multiview``. Draws ``np.random.rand()`` exactly when the reference does
+    (lines 256 / 273: only when the first view is at least ``length`` long and ``random_trim_nosil`` is set)."""
+    new_len = int(first_len)
+    if new_len < length:
+        return (0, length, True) if repeat_pad else (0, new_len, False)
+    start = int(np.random.rand() * (new_len - length)) if random_trim_nosil else 0
+    return start, length, False
+
+
+def multiview_gather(views, first_len, start, out_len, wrap, repeat_pad):
+    """out[k, v] = adjusted_v[(start + k) mod first_len if wrap else start + k], where adjusted_v is view v cut to
+    ``first_len`` samples or extended to it by zeros / by repetition (``_ad_length``, lines 229-241)."""
+    cols = []
+    for v in views:
+        v = np.asarray(v).reshape(-1)
+        m = start + np.arange(out_len)
+        if wrap:
+            m = m % first_len
+        if repeat_pad:
+            col = v[m % v.shape[0]]
+        else:
+            col = np.where(m < v.shape[0], v[np.minimum(m, v.shape[0] - 1)], 0)
+        cols.append(col)
+    return np.stack(cols, axis=1)
+
+
+def batch_pad_for_multiview(input_data_batch_, wav_samp_rate, length, random_trim_nosil=False, repeat_pad=False):
+    """Same signature and result as the reference function: list of (out_len, 1) arrays."""
+    first_len = input_data_batch_[0].shape[0]
+    start, out_len, wrap = multiview_crop_plan(first_len, length, random_trim_nosil, repeat_pad)
+    out = multiview_gather([x[:, 0] for x in input_data_batch_], first_len, start, out_len, wrap, repeat_pad)
+    return [out[:, v:v + 1] for v in range(out.shape[1])]
+
+
 class _Args:
     def __init__(self, **kw):
         self.__dict__.update(kw)

@@ -11,7 +11,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
        -Xptxas -v -I"$root/include" -I"$here" ${RB_EXTRA_FLAGS:-})
 objs=()
-for src in rb_fir_bank rb_dense rb_api rb_probe rb_devplan; do
+for src in rb_fir_bank rb_dense rb_api rb_probe rb_devplan rb_multiview; do
   "$NVCC" "${FLAGS[@]}" -c "$here/$src.cu" -o "$out/$name.$src.o" 2> "$out/$name.$src.ptxas.log" || { cat "$out/$name.$src.ptxas.log" >&2; exit 1; }
   objs+=("$out/$name.$src.o")
 done

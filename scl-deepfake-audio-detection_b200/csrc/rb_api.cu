@@ -175,8 +175,19 @@ int do_ssi(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
 
 // normWav: x -> out
 int do_normwav(const float* x, const int32_t* len, int B, int ld, int always, float* out, const Workspace& w, cudaStream_t st) {
-  (void)w;
-  return launch_isd_fused(x, len, B, ld, always, nullptr, nullptr, nullptr, 0.f, out, st);
+  const int rc = launch_isd_fused(x, len, B, ld, always, nullptr, nullptr, nullptr, 0.f, out, st);
+  if (rc != RB_ERR_UNSUPPORTED) return rc;
+  RB_TRY(launch_dense_stats(x, len, B, ld, w.stats_a, nullptr, 0, st));
+  FinalizeArgs fa{};
+  fa.stats = w.stats_a;
+  fa.ntiles = tiles_for(ld);
+  fa.len = len;
+  fa.always = always ? 1 : 0;
+  fa.raw = x;
+  fa.ld = ld;
+  fa.out = w.params;
+  RB_TRY(launch_finalize(fa, B, st));
+  return launch_apply_affine(x, len, B, ld, w.params, out, st);
 }
 
 }  // namespace

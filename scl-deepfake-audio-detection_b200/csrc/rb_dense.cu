@@ -203,18 +203,30 @@ isd_scatter_kernel(const float* __restrict__ raw, const int32_t* __restrict__ le
   }
 }
 
-// ---- ISD / normWav in ONE pass over HBM: one CTA per utterance -----------------------------------------------------------
+// ---- ISD / normWav in one kernel, one CTA per utterance -------------------------------------------------------------------
 // normWav(x, always) followed (optionally) by the impulse scatter and its normWav(., 0) (RawBoost.py:20-25, 76-84). Every
-// quantity is a max / min, so the result does not depend on the reduction order and equals the multi-pass path bit for bit.
-// The waveform is read from HBM once (statistics), read again while still L2-resident (apply) and written once; the impulse
-// bit mask lives in shared memory.
+// quantity is a max, so the result does not depend on the reduction order.
+// The peaks need the whole utterance before the first sample can be written, and 64600 floats do not fit one SM's shared
+// memory next to a second CTA. So thread t owns float4 chunks t, t+512, ...: the first kParkSmem of them are parked in shared
+// memory (96 KB) and the next kParkRegs in registers while the peaks are taken; only the chunks beyond (half of a 64600-sample
+// utterance) are read a second time, last-read first, while they are still in L2 (2 CTAs/SM x 148 SMs x 126 KB = 37 MB of
+// re-read footprint). HBM traffic is therefore close to the algorithmic read-once / write-once; two CTAs per SM overlap one
+// utterance's load phase with the other's store phase. The impulse bit mask lives in shared memory.
 constexpr int kFusedThreads = 512;
+constexpr int kParkSmem = 9;   // chunks per thread parked in shared memory
+constexpr int kParkRegs = 4;   // chunks per thread kept in registers
+constexpr int kParkChunks = (kParkSmem + kParkRegs) * kFusedThreads;  // float4 chunks resident on chip (32768 samples)
+constexpr int kOverU = 6;      // overflow chunks in flight per thread
+constexpr int kStash = 6528;   // impulse values kept in shared memory between the peak and the scatter (P = 10 % of 64600 = 6460)
 
-__global__ void __launch_bounds__(kFusedThreads)
+__global__ void __launch_bounds__(kFusedThreads, 2)
 isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, int always,
                  const int32_t* __restrict__ isd_off, const int32_t* __restrict__ isd_idx, const double* __restrict__ isd_fr,
                  float g_sd, float* __restrict__ out) {
-  extern __shared__ uint32_t smask[];  // [ceil(len/32)] impulse bit mask (unused without impulses)
+  extern __shared__ __align__(16) unsigned char dynsm[];
+  float4* park = reinterpret_cast<float4*>(dynsm);                                                  // [kParkSmem][512]
+  float* stash = reinterpret_cast<float*>(dynsm + (size_t)kParkSmem * kFusedThreads * 16);          // [kStash]
+  uint32_t* smask = reinterpret_cast<uint32_t*>(stash + kStash);                                    // [ceil(len/32)]
   __shared__ float red[kFusedThreads / 32][2];
   __shared__ float bc[3];
   const int u = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -224,51 +236,75 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
   float* orow = out + (size_t)u * ld;
   const bool with_isd = isd_off != nullptr;
   const int ibeg = with_isd ? isd_off[u] : 0, iend = with_isd ? isd_off[u + 1] : 0;
-  const int nwords = (len + 31) >> 5;
-  if (with_isd) {
-    for (int w = tid; w < nwords; w += kFusedThreads) smask[w] = 0u;
-    __syncthreads();
-    for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
-      const int p = isd_idx[i];
-      if (p >= 0 && p < len) atomicOr(smask + (p >> 5), 1u << (p & 31));
-    }
-    __syncthreads();
-  }
-  // pass 1: peak over all samples and over the samples no impulse touches (NaN-propagating like numpy's amax)
   const int nchunk = (len + 3) >> 2;
+
+  // streaming loads go around L1 (ld.global.cg): with ~100 KB of shared memory per CTA the L1 that is left is far smaller
+  // than the ~100 KB per CTA kept in flight here
+  auto load_chunk = [&](int c) {  // float4 chunk c of the row, zero beyond the end
+    const int p = 4 * c;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p + 3 < len) {
+      v = __ldcg(reinterpret_cast<const float4*>(row + p));
+    } else if (p < len) {
+      v.x = __ldcg(row + p);
+      if (p + 1 < len) v.y = __ldcg(row + p + 1);
+      if (p + 2 < len) v.z = __ldcg(row + p + 2);
+    }
+    return v;
+  };
+  float4 keep[kParkRegs];
+  {
+    constexpr int kHalf = (kParkSmem + 1) / 2, kRest = kParkSmem - kHalf;
+    float4 tmp[kHalf];
+#pragma unroll
+    for (int k = 0; k < kHalf; ++k) tmp[k] = load_chunk(k * kFusedThreads + tid);
+#pragma unroll
+    for (int k = 0; k < kParkRegs; ++k) keep[k] = load_chunk((kParkSmem + k) * kFusedThreads + tid);
+    if (with_isd) {  // build the impulse mask while the first loads are in flight
+      const int nwords = (len + 31) >> 5;
+      for (int w = tid; w < nwords; w += kFusedThreads) smask[w] = 0u;
+      __syncthreads();
+      for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
+        const int p = isd_idx[i];
+        if (p >= 0 && p < len) atomicOr(smask + (p >> 5), 1u << (p & 31));
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < kHalf; ++k) park[k * kFusedThreads + tid] = tmp[k];
+#pragma unroll
+    for (int k = 0; k < kRest; ++k) tmp[k] = load_chunk((kHalf + k) * kFusedThreads + tid);
+#pragma unroll
+    for (int k = 0; k < kRest; ++k) park[(kHalf + k) * kFusedThreads + tid] = tmp[k];
+  }
+  // peaks over all samples and over those no impulse touches (zero padding is neutral; NaN propagates like numpy's amax)
   float m_all = 0.f, m_unt = 0.f;
   bool nan_all = false, nan_unt = false;
-  constexpr int kU = 8;  // float4 loads in flight per thread: the pass is latency-bound otherwise
-  for (int c0 = tid; c0 < nchunk; c0 += kU * kFusedThreads) {
-    float4 v[kU];
+  auto peak_chunk = [&](const float4& v, int c) {
+    const int p = 4 * c;
+    const uint32_t hit = (with_isd && p < len) ? ((smask[p >> 5] >> (p & 31)) & 0xFu) : 0u;
+    const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int k = 0; k < kU; ++k) {
-      const int p = 4 * (c0 + k * kFusedThreads);
-      if (p + 3 < len) {
-        v[k] = __ldg(reinterpret_cast<const float4*>(row + p));
-      } else {
-        v[k].x = (p + 0 < len) ? __ldg(row + p + 0) : 0.f;
-        v[k].y = (p + 1 < len) ? __ldg(row + p + 1) : 0.f;
-        v[k].z = (p + 2 < len) ? __ldg(row + p + 2) : 0.f;
-        v[k].w = 0.f;
+    for (int q = 0; q < 4; ++q) {
+      const float a = fabsf(e[q]);
+      nan_all |= (a != a);
+      m_all = fmaxf(m_all, a);
+      if (!((hit >> q) & 1u)) {
+        nan_unt |= (a != a);
+        m_unt = fmaxf(m_unt, a);
       }
     }
+  };
 #pragma unroll
-    for (int k = 0; k < kU; ++k) {
-      const int p = 4 * (c0 + k * kFusedThreads);
-      const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-      const uint32_t hit = (with_isd && p < len) ? ((smask[p >> 5] >> (p & 31)) & 0xFu) : 0u;
+  for (int k = 0; k < kParkSmem; ++k) peak_chunk(park[k * kFusedThreads + tid], k * kFusedThreads + tid);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float a = fabsf(e[q]);  // padding lanes hold 0: neutral for a peak
-        nan_all |= (a != a);
-        m_all = fmaxf(m_all, a);
-        if (!((hit >> q) & 1u)) {
-          nan_unt |= (a != a);
-          m_unt = fmaxf(m_unt, a);
-        }
-      }
-    }
+  for (int k = 0; k < kParkRegs; ++k) peak_chunk(keep[k], (kParkSmem + k) * kFusedThreads + tid);
+  for (int c0 = kParkChunks + tid; c0 < nchunk; c0 += kOverU * kFusedThreads) {  // chunks that do not fit on chip
+    float4 v[kOverU];
+#pragma unroll
+    for (int k = 0; k < kOverU; ++k) v[k] = load_chunk(c0 + k * kFusedThreads);
+#pragma unroll
+    for (int k = 0; k < kOverU; ++k) peak_chunk(v[k], c0 + k * kFusedThreads);
   }
   if (nan_all) m_all = NAN;
   if (nan_unt) m_unt = NAN;
@@ -296,10 +332,18 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
   const float div1 = bc[0];
   float div2 = 1.f;
   if (with_isd) {
+    // the impulses, gathered once: parked samples come from shared memory, the value is stashed for the scatter below
+    __syncthreads();  // the parked chunks of other threads
+    const float* parked = reinterpret_cast<const float*>(park);
     float mt = 0.f;
     for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
       const int p = isd_idx[i];
-      if (p >= 0 && p < len) mt = fmaxf(mt, fabsf(isd_value(__fdiv_rn(__ldg(row + p), div1), g_sd, isd_fr[i])));
+      if (p >= 0 && p < len) {
+        const float xv = (p < kParkSmem * kFusedThreads * 4) ? parked[p] : __ldg(row + p);
+        const float t = isd_value(__fdiv_rn(xv, div1), g_sd, isd_fr[i]);
+        mt = fmaxf(mt, fabsf(t));
+        if (i - ibeg < kStash) stash[i - ibeg] = t;
+      }
     }
     mt = warp_max(mt);
     __syncthreads();
@@ -313,7 +357,7 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
     __syncthreads();
     div2 = bc[2];
   }
-  // pass 2: out = (x / div1) / div2 (division by 1 skipped: identity), then the impulses
+  // out = (x / div1) / div2 (division by 1 skipped: identity), then the impulses
   const int ndiv = (div1 != 1.f) + (div2 != 1.f);
   const float dv = (div1 != 1.f) ? div1 : div2;
   auto nrm = [&](float e) {
@@ -321,38 +365,41 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
     if (ndiv == 1) return __fdiv_rn(e, dv);
     return __fdiv_rn(__fdiv_rn(e, div1), div2);
   };
-  for (int c0 = tid; c0 < nchunk; c0 += kU * kFusedThreads) {
-    float4 v[kU];
-#pragma unroll
-    for (int k = 0; k < kU; ++k) {
-      const int p = 4 * (c0 + k * kFusedThreads);
-      if (p + 3 < len) {
-        v[k] = __ldg(reinterpret_cast<const float4*>(row + p));
-      } else {
-        v[k].x = (p + 0 < len) ? __ldg(row + p + 0) : 0.f;
-        v[k].y = (p + 1 < len) ? __ldg(row + p + 1) : 0.f;
-        v[k].z = (p + 2 < len) ? __ldg(row + p + 2) : 0.f;
-        v[k].w = 0.f;
-      }
+  auto store_chunk = [&](const float4& v, int c) {
+    const int p = 4 * c;
+    const float4 r = make_float4(nrm(v.x), nrm(v.y), nrm(v.z), nrm(v.w));
+    if (p + 3 < len) {
+      *reinterpret_cast<float4*>(orow + p) = r;
+    } else if (p < len) {
+      orow[p] = r.x;
+      if (p + 1 < len) orow[p + 1] = r.y;
+      if (p + 2 < len) orow[p + 2] = r.z;
     }
+  };
+  if (nchunk > kParkChunks) {  // the overflow first, from its end: that is what pass 1 left most recently in L2
+    const int span = kOverU * kFusedThreads;
+    const int nsweep = (nchunk - kParkChunks + span - 1) / span;
+    for (int sw = nsweep - 1; sw >= 0; --sw) {
+      const int c0 = kParkChunks + sw * span + tid;
+      float4 v[kOverU];
 #pragma unroll
-    for (int k = 0; k < kU; ++k) {
-      const int p = 4 * (c0 + k * kFusedThreads);
-      const float4 r = make_float4(nrm(v[k].x), nrm(v[k].y), nrm(v[k].z), nrm(v[k].w));
-      if (p + 3 < len) {
-        *reinterpret_cast<float4*>(orow + p) = r;
-      } else {
-        if (p + 0 < len) orow[p + 0] = r.x;
-        if (p + 1 < len) orow[p + 1] = r.y;
-        if (p + 2 < len) orow[p + 2] = r.z;
-      }
+      for (int k = 0; k < kOverU; ++k) v[k] = load_chunk(c0 + k * kFusedThreads);
+#pragma unroll
+      for (int k = 0; k < kOverU; ++k) store_chunk(v[k], c0 + k * kFusedThreads);
     }
   }
+#pragma unroll
+  for (int k = 0; k < kParkRegs; ++k) store_chunk(keep[k], (kParkSmem + k) * kFusedThreads + tid);
+#pragma unroll
+  for (int k = 0; k < kParkSmem; ++k) store_chunk(park[k * kFusedThreads + tid], k * kFusedThreads + tid);
   if (with_isd) {
-    __syncthreads();  // impulse positions overwrite what the dense pass just stored
+    __syncthreads();  // impulse positions overwrite what the dense pass just stored (merged in L2 before reaching HBM)
     for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
       const int p = isd_idx[i];
-      if (p >= 0 && p < len) orow[p] = __fdiv_rn(isd_value(__fdiv_rn(__ldg(row + p), div1), g_sd, isd_fr[i]), div2);
+      if (p >= 0 && p < len) {
+        const float t = (i - ibeg < kStash) ? stash[i - ibeg] : isd_value(__fdiv_rn(__ldg(row + p), div1), g_sd, isd_fr[i]);
+        orow[p] = __fdiv_rn(t, div2);
+      }
     }
   }
 }
@@ -444,9 +491,11 @@ namespace rb {
 int launch_isd_fused(const float* x, const int32_t* len, int B, int ld, int always, const int32_t* isd_off, const int32_t* isd_idx,
                      const double* isd_fr, float g_sd, float* out, cudaStream_t st) {
   if (B <= 0) return RB_OK;
-  const size_t smem = isd_off ? ((size_t)(ld + 31) / 32) * 4 : 0;
-  if (smem > 200 * 1024) return RB_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(isd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)kParkSmem * kFusedThreads * 16 + kStash * 4 + (isd_off ? ((size_t)(ld + 31) / 32) * 4 : 0);
+  if (smem > 113 * 1024) return RB_ERR_UNSUPPORTED;  // keeps two CTAs per SM; longer rows take the multi-pass path
+  RB_CUDA(cudaFuncSetAttribute(isd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // without this the driver may pick a carve-out that holds a single CTA per SM
+  RB_CUDA(cudaFuncSetAttribute(isd_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   isd_fused_kernel<<<B, kFusedThreads, smem, st>>>(x, len, ld, always, isd_off, isd_idx, isd_fr, g_sd, out);
   RB_LAUNCH_CHECK();
   return RB_OK;

@@ -132,3 +132,54 @@ def test_lnl_consumes_80_uniforms_and_isd_plan_is_integer_exact():
     p = orc.draw_isd_plan(64600, 10)
     assert p.idx.dtype == np.int64 and len(np.unique(p.idx)) == len(p.idx) == int(64600 * (p.beta / 100))
     assert p.idx.min() >= 0 and p.idx.max() < 64600 and np.all(np.abs(p.f_r) < 1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the step after the path: batch_pad_for_multiview and the item assembly
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def mv_golden():
+    import json
+    import os
+    from conftest import GOLDEN_DIR
+    arrays = np.load(os.path.join(GOLDEN_DIR, "multiview_golden.npz"))
+    with open(os.path.join(GOLDEN_DIR, "multiview_golden.json")) as f:
+        return arrays, json.load(f)
+
+
+def test_oracle_multiview_pad_matches_reference(mv_golden):
+    from conftest import stream_digest
+    arrays, meta = mv_golden
+    assert len(meta["pad"]) == 32
+    for key, m in meta["pad"].items():
+        flat = arrays[m["input"]]
+        views, o = [], 0
+        for n in m["lens"]:
+            views.append(flat[o:o + n].reshape(n, 1))
+            o += n
+        np.random.seed(m["seed"])
+        out = orc.batch_pad_for_multiview(views, 16000, m["length"], random_trim_nosil=m["trim"], repeat_pad=m["repeat_pad"])
+        out = np.concatenate(out, axis=1)
+        assert out.shape == arrays[key].shape and out.shape[0] == m["out_len"], key
+        assert np.array_equal(out.astype(np.float64), arrays[key].astype(np.float64)), key
+        assert stream_digest() == m["stream"], f"{key}: the crop draw must consume the stream exactly like the reference"
+
+
+def test_oracle_multiview_item_matches_reference(mv_golden):
+    """RNG order of Dataset_for.__getitem__: RawBoost on the 3 vocoded copies, then on the anchor, then the shared crop."""
+    from conftest import stream_digest
+    arrays, meta = mv_golden
+    args = orc.make_args()
+    for key, m in meta["item"].items():
+        item = int(key[4:])
+        waves = [orc.synth_utterance(m["first_wave"] + k, m["L"] + 37 * k, bool(k % 2)) for k in range(4)]
+        np.random.seed(m["seed"])
+        aug_voc = [orc.process(w, 16000, args, 5) for w in waves[1:]]
+        aug_anchor = orc.process(waves[0], 16000, args, 5)
+        views = [waves[0], aug_anchor] + waves[1:] + aug_voc
+        out = orc.batch_pad_for_multiview([np.expand_dims(v, 1) for v in views], 16000, m["trim"], random_trim_nosil=True,
+                                          repeat_pad=True)
+        out = np.concatenate(out, axis=1).astype(np.float32)
+        assert list(out.shape) == m["shape"]
+        assert np.max(np.abs(out.astype(np.float64) - arrays[key])) <= 1e-6, (key, item)
+        assert stream_digest() == m["stream"]
