@@ -129,7 +129,8 @@ int do_lnl(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
     tail.isd_fr = pl->isd_fr;
     tail.g_sd = pl->g_sd;
   }
-  return launch_fir_bank(x, len, B, ld, pl->lnl_taps, pl->lnl_tap_off, pl->n_f, 1, 1, w.buf0, w.stats_a,
+  // the raw sum goes into `out` itself and is finalised in place while still in L2: no intermediate buffer reaches HBM
+  return launch_fir_bank(x, len, B, ld, pl->lnl_taps, pl->lnl_tap_off, pl->n_f, 1, 1, out, w.stats_a,
                          with_isd ? w.mask : nullptr, w.mask_ld, tail, st);
 }
 
@@ -170,7 +171,8 @@ int do_ssi(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
   tail.out = out;
   tail.aux = x;
   tail.snr_db = pl->ssi_snr_db;
-  return launch_fir_bank(pl->ssi_noise, len, B, ld, pl->ssi_taps, pl->ssi_tap_off, 1, 1, 0, w.buf0, w.stats_a, nullptr, 0, tail, st);
+  // the coloured noise goes into `out` and is mixed in place while still in L2
+  return launch_fir_bank(pl->ssi_noise, len, B, ld, pl->ssi_taps, pl->ssi_tap_off, 1, 1, 0, out, w.stats_a, nullptr, 0, tail, st);
 }
 
 // normWav: x -> out

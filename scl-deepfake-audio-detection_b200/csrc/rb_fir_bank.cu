@@ -376,6 +376,10 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       if (ndiv == 1) return __fdiv_rn(d, dv);
       return __fdiv_rn(__fdiv_rn(d, pr.div1), pr.div2);
     };
+    // When the raw sum was written into the output buffer itself (out == y: no intermediate ever reaches HBM) the impulse
+    // positions must survive the dense pass untouched, because the scatter starts from the raw value.
+    const bool keep_hits = with_isd && (orow == raw) && mask != nullptr;
+    const uint32_t* mrow = keep_hits ? mask + (size_t)u * mask_ld : nullptr;
     constexpr int kU = 4;  // chunks in flight per thread: the reads come from L2, keep several outstanding
     for (int c0 = tid; c0 < nchunk; c0 += kU * kThreads) {
       float4 v[kU];
@@ -394,7 +398,14 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
 #pragma unroll
       for (int k = 0; k < kU; ++k) {
         const int p = 4 * (c0 + k * kThreads);
-        const float4 r = make_float4(aff(v[k].x), aff(v[k].y), aff(v[k].z), aff(v[k].w));
+        float4 r = make_float4(aff(v[k].x), aff(v[k].y), aff(v[k].z), aff(v[k].w));
+        if (keep_hits && p < len) {  // in place: impulse positions keep the raw value for the scatter below
+          const uint32_t hit = (__ldg(mrow + (p >> 5)) >> (p & 31)) & 0xFu;
+          if (hit & 1u) r.x = v[k].x;
+          if (hit & 2u) r.y = v[k].y;
+          if (hit & 4u) r.z = v[k].z;
+          if (hit & 8u) r.w = v[k].w;
+        }
         if (p + 3 < len) {
           *reinterpret_cast<float4*>(orow + p) = r;
         } else {

@@ -1,9 +1,10 @@
-# full GPU check: tests, smoke, bench (default + chunk sweep)
+# full GPU check: tests, smoke, default bench, per-algo values, ncu evidence
+tag=${1:-r01v3}
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
-for ch in 0 148 296; do
-  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --host-chunk $ch > gpurun_out/bench_chunk$ch.log 2>&1; echo "bench chunk=$ch rc=$?"
-  tail -1 gpurun_out/bench_chunk$ch.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('value',d['value'],'e2e',d['e2e']['value'], d['e2e']['ms_per_step'],'copy+kern',d['e2e']['copy_and_kernels_only_value'])" || tail -5 gpurun_out/bench_chunk$ch.log
-done
+timeout 900 python bench.py > gpurun_out/${tag}_bench_default.json 2> gpurun_out/${tag}_bench_default.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/${tag}_bench_default.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>&1; echo "ref rc=$?"; cut -c1-200 gpurun_out/${tag}_bench_reference.json
+bash scripts/gpu_algos.sh
+bash scripts/gpu_profile.sh $tag
