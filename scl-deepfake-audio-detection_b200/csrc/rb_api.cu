@@ -332,8 +332,9 @@ struct rb_ctx {
   int device;
   int sm_count;
   int chunk;  // utterances per pipeline chunk (0: four per SM)
-  cudaStream_t s_in, s_plan, s_cmp, s_out;
-  cudaEvent_t ev_meta;
+  int plan_mode;  // device planner: 0 = on its own streams beside the kernels (default), 1 = in line on the kernels' stream
+  cudaStream_t s_in, s_plan, s_apply, s_cmp, s_out;
+  cudaEvent_t ev_meta, ev_body[3];
   Slot slot[kSlots];
   char* meta = nullptr;  // per-call device copy of len[] and seeds[]
   size_t meta_bytes = 0;
@@ -384,6 +385,8 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
   if (devplan && (!args || !seeds)) return RB_ERR_INVALID_ARG;
   const int chunk = std::max(1, std::min(B, c->chunk > 0 ? c->chunk : 4 * c->sm_count));
   const int n_f = plan ? plan->n_f : (args ? args->N_f : 0);
+  // Equal chunks. (A short-chunk ramp at the start -- a quarter, a half, then full chunks -- gets the first results out
+  // earlier but measured 2 ms slower overall at B = 4096: small launches run the latency-bound planner kernels less efficiently.)
   std::vector<int> first;  // first utterance of each chunk, plus B
   for (int u = 0; u < B; u += chunk) first.push_back(u);
   first.push_back(B);
@@ -463,30 +466,44 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     }
   };
   mark(0, c->s_in);
-  // Device planner: the plans need only lengths and seeds, so the planner stream runs ahead of the copies. The first chunk is
-  // planned on its own (the kernels can start as soon as its waveforms are in); the stream-replay stage of all other
-  // utterances is one launch (it is latency-bound: one warp per utterance, thousands in flight), after which each chunk only
-  // needs its swaps applied.
+  // Device planner. The plans need only lengths and seeds. Its kernels are latency-bound (one warp per utterance) and are
+  // issued in three pieces -- chunk 0, chunk 1, everything else -- so that the first results leave early (the call is bound by
+  // the copy-out stream, which starts with the first filtered chunk).
+  //   plan_mode 0 (default): stream replay on s_plan, swap application on s_apply, beside the kernels. The overlap is partial:
+  //     the planner's CTAs take shared memory / registers from the FIR-bank CTAs while they are resident, so planner and
+  //     filtering largely take turns (B = 4096: 31.0 ms per call).
+  //   plan_mode 1: in line on the kernels' stream, each piece right before the first chunk that needs it; the planner then
+  //     never shares an SM with the FIR-bank kernel (B = 4096: 32.6 ms per call). Kept for measurement.
+  int piece_end[3] = {nchunks, nchunks, nchunks};
+  int npieces = 1;
+  if (devplan && !use_ssi && nchunks >= 3) {  // SSI tap offsets need the stream positions of every utterance: one piece
+    npieces = 3;
+    piece_end[0] = 1;
+    piece_end[1] = 2;
+  }
+  auto plan_piece = [&](int pc, cudaStream_t s_body, cudaStream_t s_swap) -> int {
+    const int cb = pc ? piece_end[pc - 1] : 0;
+    const int u0 = first[cb], u1 = first[piece_end[pc]];
+    RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, c->planmem, u0, u1 - u0, s_body));
+    if (use_ssi) RB_TRY(devplan_end(args, algo, B, ld, c->planmem, s_body));
+    if (s_swap != s_body) {
+      RB_CUDA(cudaEventRecord(c->ev_body[pc], s_body));
+      RB_CUDA(cudaStreamWaitEvent(s_swap, c->ev_body[pc], 0));
+    }
+    for (int ci = cb; ci < piece_end[pc]; ++ci) {
+      RB_TRY(devplan_apply(args, algo, B, ld, d_len, c->planmem, first[ci], first[ci + 1] - first[ci], s_swap));
+      if (s_swap != c->s_cmp) RB_CUDA(cudaEventRecord(c->ev_planned[ci], s_swap));
+      mark(2, s_swap);
+    }
+    return RB_OK;
+  };
   rb_plan whole;
   memset(&whole, 0, sizeof(whole));
   if (devplan) {
-    const int c0 = first[1];
-    RB_TRY(devplan_begin(args, algo, B, ld, d_len, d_seeds, c->planmem, c->planmem_bytes, &whole, c->s_plan));
-    if (use_ssi) {  // SSI tap offsets need the stream positions of every utterance
-      RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, c->planmem, 0, B, c->s_plan));
-      RB_TRY(devplan_end(args, algo, B, ld, c->planmem, c->s_plan));
-    } else {
-      RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, c->planmem, 0, c0, c->s_plan));
-    }
-    RB_TRY(devplan_apply(args, algo, B, ld, d_len, c->planmem, 0, c0, c->s_plan));
-    RB_CUDA(cudaEventRecord(c->ev_planned[0], c->s_plan));
-    mark(2, c->s_plan);
-    if (!use_ssi) RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, c->planmem, c0, B - c0, c->s_plan));
-    for (int ci = 1; ci < nchunks; ++ci) {
-      RB_TRY(devplan_apply(args, algo, B, ld, d_len, c->planmem, first[ci], first[ci + 1] - first[ci], c->s_plan));
-      RB_CUDA(cudaEventRecord(c->ev_planned[ci], c->s_plan));
-      mark(2, c->s_plan);
-    }
+    const cudaStream_t s0 = c->plan_mode ? c->s_cmp : c->s_plan;
+    RB_TRY(devplan_begin(args, algo, B, ld, d_len, d_seeds, c->planmem, c->planmem_bytes, &whole, s0));
+    if (!c->plan_mode)
+      for (int pc = 0; pc < npieces; ++pc) RB_TRY(plan_piece(pc, c->s_plan, c->s_apply));
   }
   for (int ci = 0; ci < nchunks; ++ci) {
     Slot& sl = c->slot[ci % kSlots];
@@ -551,7 +568,12 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
         dp.ssi_tap_off = whole.ssi_tap_off + u0;
         dp.ssi_snr_db = whole.ssi_snr_db + u0;
       }
-      RB_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_planned[ci], 0));
+      if (c->plan_mode) {
+        for (int pc = 0; pc < npieces; ++pc)
+          if (ci == (pc ? piece_end[pc - 1] : 0)) RB_TRY(plan_piece(pc, c->s_cmp, c->s_cmp));
+      } else {
+        RB_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_planned[ci], 0));
+      }
     }
     if (!devplan) mark(2, c->s_in);
     RB_CUDA(cudaStreamWaitEvent(c->s_cmp, sl.ev_in, 0));
@@ -608,14 +630,18 @@ int rb_ctx_create(rb_ctx** out, int device) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   c->chunk = 0;
+  c->plan_mode = 0;
   c->h2d = c->d2h = 0;
-  c->s_in = c->s_plan = c->s_cmp = c->s_out = nullptr;
+  c->s_in = c->s_plan = c->s_apply = c->s_cmp = c->s_out = nullptr;
   c->ev_meta = nullptr;
+  for (cudaEvent_t& e : c->ev_body) e = nullptr;
   // copies and the (latency-bound, few-warp) planner kernels get priority over the FIR kernel's CTAs
   int prio_lo = 0, prio_hi = 0;
   cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  for (cudaStream_t* s : {&c->s_in, &c->s_plan, &c->s_out})
+  for (cudaStream_t* s : {&c->s_in, &c->s_plan, &c->s_apply, &c->s_out})
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_hi);
+  for (cudaEvent_t& ev : c->ev_body)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->s_cmp, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_meta, cudaEventDisableTiming);
   for (Slot& sl : c->slot)
@@ -642,7 +668,9 @@ int rb_ctx_destroy(rb_ctx* c) {
   if (c->planmem) cudaFree(c->planmem);
   for (cudaEvent_t e : c->ev_planned) cudaEventDestroy(e);
   if (c->ev_meta) cudaEventDestroy(c->ev_meta);
-  for (cudaStream_t s : {c->s_in, c->s_plan, c->s_cmp, c->s_out})
+  for (cudaEvent_t e : c->ev_body)
+    if (e) cudaEventDestroy(e);
+  for (cudaStream_t s : {c->s_in, c->s_plan, c->s_apply, c->s_cmp, c->s_out})
     if (s) cudaStreamDestroy(s);
   delete c;
   return RB_OK;
@@ -651,6 +679,12 @@ int rb_ctx_destroy(rb_ctx* c) {
 int rb_ctx_set_chunk(rb_ctx* c, int utterances) {
   if (!c || utterances < 0) return RB_ERR_INVALID_ARG;
   c->chunk = utterances;
+  return RB_OK;
+}
+
+int rb_ctx_set_plan_mode(rb_ctx* c, int mode) {
+  if (!c || (mode != 0 && mode != 1)) return RB_ERR_INVALID_ARG;
+  c->plan_mode = mode;
   return RB_OK;
 }
 

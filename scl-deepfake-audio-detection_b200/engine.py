@@ -221,6 +221,10 @@ class Engine:
         """Utterances per pipeline chunk of the host-buffer entry points (0 = default: four per SM)."""
         _lib.check(self.lib.rb_ctx_set_chunk(self._host_ctx(), int(utterances)), "rb_ctx_set_chunk")
 
+    def set_host_plan_mode(self, mode: int) -> None:
+        """Device planner placement in :meth:`process_host_seeded`: 0 = on its own streams beside the kernels (default), 1 = in line."""
+        _lib.check(self.lib.rb_ctx_set_plan_mode(self._host_ctx(), int(mode)), "rb_ctx_set_plan_mode")
+
     def process_host_seeded(self, algo: int, x: np.ndarray, lengths: np.ndarray, seeds, sr, args,
                             out: Optional[np.ndarray] = None) -> np.ndarray:
         """Host waveforms in, host results out, plans drawn ON THE DEVICE from per-utterance seeds
