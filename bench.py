@@ -127,7 +127,7 @@ def reference_arm(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -446,7 +446,7 @@ def gpu_arm(a):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -456,6 +456,28 @@ def _plan_jobs(lengths, args, algo, seeds, workers):
     n = len(lengths)
     step = max(1, (n + 4 * workers - 1) // (4 * workers))
     return [(list(lengths[i:i + step]), 16000, vars(args), algo, list(seeds[i:i + step])) for i in range(0, n, step)]
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything libraries print to fd 1 (e.g. NCCL's version banner) to stderr; rank 0's JSON line goes to the real
+    stdout through :func:`emit`, so stdout carries exactly one line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -477,6 +499,7 @@ def main():
     ap.add_argument("--cpu-per-core", type=int, default=8, help="utterances per host core per CPU-baseline step")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    quiet_stdout()
     if a.impl == "reference":
         reference_arm(a)
     else:

@@ -32,7 +32,11 @@ def init_process_group(backend: str):
         return
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29500")
-    dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    kw = {}
+    if backend == "nccl":  # bind the communicator to this rank's GPU (LOCAL_RANK) instead of letting NCCL guess
+        import torch
+        kw["device_id"] = torch.device("cuda", env_rank_world()[1])
+    dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
 
 
 def barrier():
