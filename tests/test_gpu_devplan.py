@@ -152,3 +152,28 @@ def test_seeded_host_entry_against_oracle(eng):
         np.random.seed(seeds[u])
         ref = orc.process(w, 16000, ARGS, 5)
         assert np.max(np.abs(y[u, :w.shape[0]].astype(np.float64) - ref)) <= 1e-5
+
+
+def test_device_plan_many_seeds_full_length(eng, P):
+    """512 utterances of the benchmark's size: device-drawn integers and impulse gains against the native host planner
+    (itself pinned to numpy by tests/test_host_logic.py), and against numpy itself on a subset."""
+    from scl_deepfake_audio_detection_b200.native_planner import NativePlanner
+    B = 512
+    lengths = [64600] * B
+    seeds = [(2654435761 * (u + 1)) % 2 ** 32 for u in range(B)]
+    _, got, ld = device_plan(eng, lengths, seeds, 5)
+    ref = NativePlanner(threads=0, pinned=False).draw(lengths, 16000, ARGS, 5, seeds=seeds, ld=ld, copy=True)
+    assert np.array_equal(ref.lnl_tap_off, got.lnl_tap_off)
+    assert np.array_equal(ref.isd_off, got.isd_off)
+    assert np.array_equal(ref.isd_idx, got.isd_idx)
+    assert np.array_equal(ref.isd_fr, got.isd_fr)
+    assert ulp_err(got.lnl_taps, ref.lnl_taps) <= 1.0
+    sub = P.draw_batch(lengths[:8], 16000, ARGS, 5, seeds=seeds[:8], ld=ld)
+    n8 = int(sub.isd_off[-1])
+    assert np.array_equal(sub.isd_off, got.isd_off[:9]) and np.array_equal(sub.isd_idx, got.isd_idx[:n8])
+    assert np.array_equal(sub.isd_fr, got.isd_fr[:n8])
+    assert np.array_equal(sub.lnl_tap_off, got.lnl_tap_off[:8 * 5 + 1])
+    # every impulse position is a valid, unique sample index of its utterance
+    for u in range(0, B, 37):
+        idx = got.isd_idx[got.isd_off[u]:got.isd_off[u + 1]]
+        assert idx.min(initial=0) >= 0 and idx.max(initial=0) < 64600 and np.unique(idx).size == idx.size
