@@ -278,9 +278,11 @@ scan_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ off) {
 //      in cuts[chunk] starts a new conflict-free group.
 // perm_apply_kernel (one warp per SM, the permutation as uint16 in shared memory) then only loads, swaps and stores group
 // by group.
+constexpr int kDupWords = 128;  // 4096-bit duplicate filter per warp (keeps 7 CTAs = 28 utterances per SM)
 constexpr int kBodyWarps = 4;  // 30 KB of MT19937 state per CTA: up to 7 CTAs = 28 utterances in flight per SM
 
-__device__ void shuffle_scan_warp(MtStream& s, int L, uint16_t* __restrict__ jseq, uint32_t* __restrict__ cuts, int lane) {
+__device__ void shuffle_scan_warp(MtStream& s, int L, uint16_t* __restrict__ jseq, uint32_t* __restrict__ cuts, uint32_t* dupset,
+                                  int lane) {
   const uint32_t lt = (1u << lane) - 1u;
   int i = L - 1;
   while (i >= 1) {
@@ -311,34 +313,51 @@ __device__ void shuffle_scan_warp(MtStream& s, int L, uint16_t* __restrict__ jse
   }
   __syncwarp();  // jseq was written by other lanes of this warp
   const int nsteps = L - 1;
-  constexpr int kAhead = 4;  // chunks whose targets are loaded before the first of them is examined (they come back from L2)
+  // Conflicts are rare (7 % of the chunks) and MATCH.ANY is slow (about a hundred cycles of a per-SM unit each), so every
+  // chunk first goes through an exact-negative filter: each step sets the bit of its target in a 4096-bit shared-memory
+  // set (atomicOr returns the previous word: a set bit means another step of the chunk hashed to the same place) and a
+  // vote tells whether any step targets one of the chunk's own slots. Only chunks that trip either test (hash collisions
+  // included, ~12 %) take the exact MATCH / REDUX path. The targets of the next four chunks are already on their way from L2.
+  constexpr int kAhead = 4;
+  int jn[kAhead];
+#pragma unroll
+  for (int q = 0; q < kAhead; ++q) {
+    const int k = q * 32 + lane;
+    jn[q] = k < nsteps ? (int)jseq[k] : 0;
+  }
   for (int c0 = 0; c0 * 32 < nsteps; c0 += kAhead) {
     int jj[kAhead];
 #pragma unroll
     for (int q = 0; q < kAhead; ++q) {
-      const int k = (c0 + q) * 32 + lane;
-      jj[q] = k < nsteps ? (int)jseq[k] : 0;
+      jj[q] = jn[q];
+      const int k = (c0 + kAhead + q) * 32 + lane;
+      jn[q] = k < nsteps ? (int)jseq[k] : 0;
     }
 #pragma unroll
     for (int q = 0; q < kAhead; ++q) {
       const int c = c0 + q;
       if (c * 32 >= nsteps) break;
       const bool valid = c * 32 + lane < nsteps;
-      const int i0 = (L - 1) - c * 32;       // slot of lane 0; lane t owns slot i0 - t
+      const int i0 = (L - 1) - c * 32;  // slot of lane 0; lane t owns slot i0 - t
       const int j = jj[q];
+      const bool hits_slot = valid && j > i0 - 32 && j != i0 - lane;  // targets the slot of lane i0 - j of this chunk
+      const uint32_t old = valid ? atomicOr(dupset + ((j >> 5) & (kDupWords - 1)), 1u << (j & 31)) : 0u;
+      const uint32_t suspicious = __ballot_sync(kFull, hits_slot || (valid && ((old >> (j & 31)) & 1u)));
+      if (valid) atomicAnd(dupset + ((j >> 5) & (kDupWords - 1)), ~(1u << (j & 31)));  // leave the set empty again
       uint32_t cut = 0;
-      int start = 0;
-      for (;;) {
-        const bool active = valid && lane >= start;
-        const uint32_t same = __match_any_sync(kFull, active ? (uint32_t)j : (0x10000u + (uint32_t)lane));
-        uint32_t tbit = 0;
-        if (active && j > i0 - 32 && j != i0 - lane) tbit = 1u << (i0 - j);  // this step targets the slot of lane i0 - j
-        const uint32_t tmap = __reduce_or_sync(kFull, tbit);
-        const bool bad = active && (((same & lt) != 0u) || ((tmap >> lane) & 1u));
-        const uint32_t badmask = __ballot_sync(kFull, bad);
-        if (!badmask) break;
-        start = __ffs(badmask) - 1;          // > previous start: the first active lane has nothing before it
-        cut |= 1u << start;
+      if (suspicious) {
+        int start = 0;
+        for (;;) {
+          const bool active = valid && lane >= start;
+          const uint32_t same = __match_any_sync(kFull, active ? (uint32_t)j : (0x10000u + (uint32_t)lane));
+          uint32_t tbit = 0;
+          if (active && j > i0 - 32 && j != i0 - lane) tbit = 1u << (i0 - j);
+          const uint32_t tmap = __reduce_or_sync(kFull, tbit);
+          const uint32_t badmask = __ballot_sync(kFull, active && (((same & lt) != 0u) || ((tmap >> lane) & 1u)));
+          if (!badmask) break;
+          start = __ffs(badmask) - 1;  // grows every time: the first active lane has nothing before it
+          cut |= 1u << start;
+        }
       }
       if (lane == 0) cuts[c] = cut;
     }
@@ -351,9 +370,12 @@ plan_body_kernel(rb_args a, int algo, int B, int ld, int jld, const int32_t* __r
                  uint32_t* __restrict__ cuts_all, int cuts_ld, float* __restrict__ ssi_noise, double* __restrict__ ssi_params,
                  int32_t* __restrict__ ssi_cnt, float* __restrict__ ssi_snr) {
   __shared__ MtSmem msm[kBodyWarps];
+  __shared__ uint32_t dupset[kBodyWarps][kDupWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = blockIdx.x * kBodyWarps + warp;
   if (u >= B) return;
+  for (int w = lane; w < kDupWords; w += 32) dupset[warp][w] = 0u;
+  __syncwarp();
   const int L = len_arr[u];
   MtStream s;
   s.sm = &msm[warp];
@@ -362,7 +384,7 @@ plan_body_kernel(rb_args a, int algo, int B, int ld, int jld, const int32_t* __r
   if (uses_isd(algo)) {
     s.advance(2, lane);  // beta (the head kernel turned it into the impulse count)
     const int beg = isd_off[u], n = isd_off[u + 1] - beg;
-    shuffle_scan_warp(s, L, jseq_all + (size_t)u * jld, cuts_all + (size_t)u * cuts_ld, lane);
+    shuffle_scan_warp(s, L, jseq_all + (size_t)u * jld, cuts_all + (size_t)u * cuts_ld, dupset[warp], lane);
     // f_r = (2*rand(n) - 1) * (2*rand(n) - 1)   (RawBoost.py:80)
     for (int pass = 0; pass < 2; ++pass) {
       for (int base = 0; base < n; base += 32) {
