@@ -301,6 +301,13 @@ def batch_pad_for_multiview(input_data_batch_, wav_samp_rate, length, random_tri
     return [out[:, v:v + 1] for v in range(out.shape[1])]
 
 
+def reverb_convolve(data, rir_data):
+    """Arithmetic of ``ReverbAugmentor.transform`` (/root/reference/datautils/audio_augmentor/reverb.py:39-42)."""
+    reverberate = np.convolve(np.asarray(data, dtype=np.float64), np.asarray(rir_data, dtype=np.float64))
+    reverberate /= np.max(np.abs(reverberate))
+    return reverberate
+
+
 class _Args:
     def __init__(self, **kw):
         self.__dict__.update(kw)

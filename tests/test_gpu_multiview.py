@@ -88,3 +88,17 @@ def test_item_views_match_reference_item(eng, mv):
         # the untouched views (anchor, vocoded copies) are pure copies
         for col in (0, 2, 3, 4):
             assert np.array_equal(got[:, col], arrays[key][:, col])
+
+
+@pytest.mark.parametrize("L,K", [(64600, 8000), (16000, 1), (5000, 513), (300, 2049), (1, 700)])
+def test_reverb_view_matches_reference_arithmetic(eng, L, K):
+    """np.convolve(data, rir) + peak normalisation (audio_augmentor/reverb.py:39-42) on the FIR machinery."""
+    from scl_deepfake_audio_detection_b200 import reverb
+    rs = np.random.RandomState(L + K)
+    x = (0.2 * rs.standard_normal(L)).astype(np.float32)
+    rir = (rs.standard_normal(K) * np.exp(-np.arange(K) / max(1.0, K / 6.0))).astype(np.float32)
+    y = reverb.reverb_convolve(x, rir)
+    ref = orc.reverb_convolve(x, rir)
+    assert y.dtype == np.float32 and y.shape == ref.shape == (L + K - 1,)
+    assert np.max(np.abs(y.astype(np.float64) - ref)) <= 1e-5
+    assert abs(float(np.max(np.abs(y))) - 1.0) <= 1e-6
