@@ -88,8 +88,11 @@ typedef struct rb_plan {
   const float* ssi_snr_db;
 } rb_plan;
 
-/* Device workspace (bytes) that rb_* entry points need for a batch of B rows of stride ld. */
+/* Device workspace (bytes) that rb_* entry points need for a batch of B rows of stride ld: rb_workspace_bytes covers every
+ * algo; rb_workspace_bytes_for is what one algo needs (algos 1, 2, 3 and 5 need no waveform-sized scratch at all, the
+ * chained algos 4, 6, 7 one buffer, algo 8 three). */
 RB_API size_t rb_workspace_bytes(int B, int ld);
+RB_API size_t rb_workspace_bytes_for(int algo, int B, int ld);
 
 /* ---- a-4  filterFIR(x, b)  (RawBoost.py:51-56), batched --------------------------------------------------
  * y[u][n] = sum_k b_u[k] * x[u][n + (K_u+1)/2 - k],  x == 0 outside [0, len[u]);  any K_u >= 1.

@@ -15,7 +15,7 @@ RB_ABI_VERSION = 1
 
 #: every symbol ``include/rawboost_b200.h`` declares (checked by the CPU test-suite against the header)
 SYMBOLS = (
-    "rb_error_string", "rb_abi_version", "rb_workspace_bytes", "rb_filter_fir", "rb_normwav", "rb_lnl", "rb_isd",
+    "rb_error_string", "rb_abi_version", "rb_workspace_bytes", "rb_workspace_bytes_for", "rb_filter_fir", "rb_normwav", "rb_lnl", "rb_isd",
     "rb_ssi", "rb_process", "rb_ctx_create", "rb_ctx_destroy", "rb_process_host", "rb_ctx_last_traffic",
     "rb_probe_fp32", "rb_launch_count", "rb_profile_enable", "rb_profile_read", "rb_planner_create", "rb_planner_destroy",
     "rb_planner_draw", "rb_devplan_bytes", "rb_devplan_draw", "rb_process_host_seeded",
@@ -93,6 +93,8 @@ def load() -> C.CDLL:
     lib.rb_abi_version.argtypes = []
     lib.rb_workspace_bytes.restype = sz
     lib.rb_workspace_bytes.argtypes = [i32, i32]
+    lib.rb_workspace_bytes_for.restype = sz
+    lib.rb_workspace_bytes_for.argtypes = [i32, i32, i32]
     lib.rb_filter_fir.restype = i32
     lib.rb_filter_fir.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp]
     lib.rb_normwav.restype = i32

@@ -61,13 +61,17 @@ struct Workspace {
   uint32_t* counters;  // per-utterance tile arrival counters of the fused FIR tail
   uint32_t* mask;
   int mask_ld;
-  float* buf0;  // raw FIR-bank output / coloured noise
-  float* buf1;  // intermediate waveform of chained algos
+  float* buf1;  // intermediate waveform of the chained algos 4, 6, 7, 8
   float* buf2;  // second branch of algo 8
+  float* buf0;  // sum of the two branches of algo 8
   size_t bytes;
 };
 
-Workspace carve(void* base, int B, int ld) {
+// Waveform-sized scratch buffers an algo needs: the single-operator algos (1, 2, 3) and the fused LnL -> ISD (5) write into
+// the output buffer itself; the chains 4, 6, 7 hold one intermediate waveform; algo 8 two branches and their sum.
+inline int scratch_waveforms(int algo) { return algo == 8 ? 3 : (algo == 4 || algo == 6 || algo == 7) ? 1 : 0; }
+
+Workspace carve(void* base, int B, int ld, int nbuf) {
   Workspace w;
   const int ntiles = tiles_for(ld);
   size_t off = 0;
@@ -83,9 +87,9 @@ Workspace carve(void* base, int B, int ld) {
   w.counters = (uint32_t*)take((size_t)B * sizeof(uint32_t));
   w.mask_ld = mask_ld_for(ld);
   w.mask = (uint32_t*)take((size_t)B * w.mask_ld * sizeof(uint32_t));
-  w.buf0 = (float*)take((size_t)B * ld * sizeof(float));
-  w.buf1 = (float*)take((size_t)B * ld * sizeof(float));
-  w.buf2 = (float*)take((size_t)B * ld * sizeof(float));
+  w.buf1 = nbuf >= 1 ? (float*)take((size_t)B * ld * sizeof(float)) : nullptr;
+  w.buf2 = nbuf >= 2 ? (float*)take((size_t)B * ld * sizeof(float)) : nullptr;
+  w.buf0 = nbuf >= 3 ? (float*)take((size_t)B * ld * sizeof(float)) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -98,10 +102,10 @@ int check_batch(const void* x, const int32_t* len, int B, int ld, const void* y)
   return RB_OK;
 }
 
-int check_ws(void* ws, size_t ws_bytes, int B, int ld, Workspace* out) {
+int check_ws(void* ws, size_t ws_bytes, int B, int ld, int algo, Workspace* out) {
   if (B == 0 || ld == 0) return RB_OK;
   if (!ws || ((uintptr_t)ws & 255u)) return ws ? RB_ERR_ALIGNMENT : RB_ERR_WORKSPACE;
-  *out = carve(ws, B, ld);
+  *out = carve(ws, B, ld, scratch_waveforms(algo));
   if (out->bytes > ws_bytes) return RB_ERR_WORKSPACE;
   return RB_OK;
 }
@@ -218,7 +222,12 @@ int rb_abi_version(void) { return RB_ABI_VERSION; }
 
 size_t rb_workspace_bytes(int B, int ld) {
   if (B <= 0 || ld <= 0) return 0;
-  return carve(nullptr, B, ld).bytes;
+  return carve(nullptr, B, ld, 3).bytes;
+}
+
+size_t rb_workspace_bytes_for(int algo, int B, int ld) {
+  if (B <= 0 || ld <= 0) return 0;
+  return carve(nullptr, B, ld, scratch_waveforms(algo)).bytes;
 }
 
 uint64_t rb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -261,7 +270,7 @@ int rb_normwav(const float* x, const int32_t* len, int B, int ld, int always, fl
   RB_TRY(check_batch(x, len, B, ld, y));
   if (B == 0 || ld == 0) return RB_OK;
   Workspace w;
-  RB_TRY(check_ws(workspace, workspace_bytes, B, ld, &w));
+  RB_TRY(check_ws(workspace, workspace_bytes, B, ld, 0, &w));
   return do_normwav(x, len, B, ld, always, y, w, (cudaStream_t)stream);
 }
 
@@ -289,7 +298,7 @@ int rb_process(int algo, const float* x, const int32_t* len, int B, int ld, cons
   }
   if (x == y) return RB_ERR_INVALID_ARG;
   Workspace w;
-  RB_TRY(check_ws(workspace, workspace_bytes, B, ld, &w));
+  RB_TRY(check_ws(workspace, workspace_bytes, B, ld, algo, &w));
   switch (algo) {
     case 1: return do_lnl(x, len, B, ld, plan, false, y, w, st);
     case 2: return do_isd(x, len, B, ld, plan, y, w, st);
@@ -418,7 +427,7 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
 
   // slot layout for the largest chunk
   const size_t wave = (size_t)chunk * ld * sizeof(float);
-  const size_t ws_bytes = active ? rb_workspace_bytes(chunk, ld) : 0;
+  const size_t ws_bytes = active ? rb_workspace_bytes_for(algo, chunk, ld) : 0;
   const size_t dp_bytes = devplan ? rb_devplan_bytes(args, algo, B, ld) : 0;
   if (devplan && dp_bytes == 0) return RB_ERR_UNSUPPORTED;
   if (dp_bytes > c->planmem_bytes) {

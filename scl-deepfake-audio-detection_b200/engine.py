@@ -46,8 +46,9 @@ class Engine:
         self._ctx = None
 
     # -- memory ---------------------------------------------------------------------------------------
-    def workspace(self, B: int, ld: int) -> torch.Tensor:
-        need = int(self.lib.rb_workspace_bytes(B, ld))
+    def workspace(self, B: int, ld: int, algo: int = 8) -> torch.Tensor:
+        """Growable device workspace, sized for what ``algo`` needs (algo 8 needs the most)."""
+        need = int(self.lib.rb_workspace_bytes_for(int(algo), B, ld))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
@@ -140,7 +141,7 @@ class Engine:
         B, ld = x.shape
         if out is None:
             out = torch.zeros_like(x)
-        ws = self.workspace(B, ld)
+        ws = self.workspace(B, ld, algo)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         ps = C.byref(plan.struct) if plan is not None else None
         with torch.cuda.device(self.device):
@@ -166,7 +167,7 @@ class Engine:
         B, ld = x.shape
         if out is None:
             out = torch.zeros_like(x)
-        ws = self.workspace(B, ld)
+        ws = self.workspace(B, ld, 0)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             rc = self.lib.rb_normwav(_ptr(x), _ptr(lengths), B, ld, int(bool(always)), _ptr(out), C.c_void_p(self._ws_ptr(ws)),
