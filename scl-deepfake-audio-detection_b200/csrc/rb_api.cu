@@ -328,7 +328,7 @@ int rb_process(int algo, const float* x, const int32_t* len, int B, int ld, cons
 // host-buffer context: a chunked three-stage pipeline (H2D | plan + kernels | D2H)
 // ---------------------------------------------------------------------------------------------------
 namespace {
-constexpr int kSlots = 4;
+constexpr int kSlots = 8;
 
 struct Slot {
   char* dev = nullptr;
@@ -394,8 +394,9 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
   if (devplan && (!args || !seeds)) return RB_ERR_INVALID_ARG;
   const int chunk = std::max(1, std::min(B, c->chunk > 0 ? c->chunk : 4 * c->sm_count));
   const int n_f = plan ? plan->n_f : (args ? args->N_f : 0);
-  // Equal chunks. (A short-chunk ramp at the start -- a quarter, a half, then full chunks -- gets the first results out
-  // earlier but measured 2 ms slower overall at B = 4096: small launches run the latency-bound planner kernels less efficiently.)
+  // Equal chunks. Shorter chunks at the start and / or the end (to get the first results out earlier, to shorten the last
+  // copy-out) were measured and do not help: with both PCIe directions busy the call is bound by the two ~22 ms copy streams
+  // and their mutual offset of one chunk's filtering.
   std::vector<int> first;  // first utterance of each chunk, plus B
   for (int u = 0; u < B; u += chunk) first.push_back(u);
   first.push_back(B);
@@ -478,11 +479,10 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
   // Device planner. The plans need only lengths and seeds. Its kernels are latency-bound (one warp per utterance) and are
   // issued in three pieces -- chunk 0, chunk 1, everything else -- so that the first results leave early (the call is bound by
   // the copy-out stream, which starts with the first filtered chunk).
-  //   plan_mode 0 (default): stream replay on s_plan, swap application on s_apply, beside the kernels. The overlap is partial:
-  //     the planner's CTAs take shared memory / registers from the FIR-bank CTAs while they are resident, so planner and
-  //     filtering largely take turns (B = 4096: 31.0 ms per call).
+  //   plan_mode 0 (default): stream replay on s_plan, swap application on s_apply, both at low priority beside the kernels.
   //   plan_mode 1: in line on the kernels' stream, each piece right before the first chunk that needs it; the planner then
-  //     never shares an SM with the FIR-bank kernel (B = 4096: 32.6 ms per call). Kept for measurement.
+  //     never shares an SM with the FIR-bank kernel. Slower (the planner's latency-bound kernels leave the SMs mostly idle
+  //     while nothing else may run); kept for measurement.
   int piece_end[3] = {nchunks, nchunks, nchunks};
   int npieces = 1;
   if (devplan && !use_ssi && nchunks >= 3) {  // SSI tap offsets need the stream positions of every utterance: one piece
@@ -644,14 +644,18 @@ int rb_ctx_create(rb_ctx** out, int device) {
   c->s_in = c->s_plan = c->s_apply = c->s_cmp = c->s_out = nullptr;
   c->ev_meta = nullptr;
   for (cudaEvent_t& e : c->ev_body) e = nullptr;
-  // copies and the (latency-bound, few-warp) planner kernels get priority over the FIR kernel's CTAs
+  // Stream priorities: copies first, then the FIR kernel's stream, the planner's streams last. The planner only needs to stay
+  // ahead of the filtering (it is ~2.5x faster per chunk), so it runs in the gaps -- while the filtering waits for the next
+  // chunk's waveforms, and in whatever an SM has left beside the FIR-bank CTAs -- instead of displacing them: measured 27.3 ms
+  // per 4096 utterances against 29.6 ms with the planner's streams on top.
   int prio_lo = 0, prio_hi = 0;
   cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  for (cudaStream_t* s : {&c->s_in, &c->s_plan, &c->s_apply, &c->s_out})
+  for (cudaStream_t* s : {&c->s_in, &c->s_out, &c->s_cmp})
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_hi);
+  for (cudaStream_t* s : {&c->s_plan, &c->s_apply})
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_lo);
   for (cudaEvent_t& ev : c->ev_body)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->s_cmp, cudaStreamNonBlocking, prio_lo);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_meta, cudaEventDisableTiming);
   for (Slot& sl : c->slot)
     for (cudaEvent_t* ev : {&sl.ev_in, &sl.ev_planned, &sl.ev_done, &sl.ev_out})
