@@ -252,15 +252,26 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
     }
     return v;
   };
+  // Everything that fits on chip is requested at once: the parked chunks go global -> shared by cp.async (no registers
+  // involved, so all nine per thread are in flight together), the kept chunks into registers. The impulse mask is built
+  // while they travel.
   float4 keep[kParkRegs];
   {
-    constexpr int kHalf = (kParkSmem + 1) / 2, kRest = kParkSmem - kHalf;
-    float4 tmp[kHalf];
 #pragma unroll
-    for (int k = 0; k < kHalf; ++k) tmp[k] = load_chunk(k * kFusedThreads + tid);
+    for (int k = 0; k < kParkSmem; ++k) {
+      const int c = k * kFusedThreads + tid;
+      float4* dst = park + c;
+      if (4 * c + 3 < len) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(row + 4 * c)
+                     : "memory");
+      } else {
+        *dst = load_chunk(c);  // the ragged last chunk and everything beyond the end (zeros)
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
     for (int k = 0; k < kParkRegs; ++k) keep[k] = load_chunk((kParkSmem + k) * kFusedThreads + tid);
-    if (with_isd) {  // build the impulse mask while the first loads are in flight
+    if (with_isd) {
       const int nwords = (len + 31) >> 5;
       for (int w = tid; w < nwords; w += kFusedThreads) smask[w] = 0u;
       __syncthreads();
@@ -268,14 +279,8 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
         const int p = isd_idx[i];
         if (p >= 0 && p < len) atomicOr(smask + (p >> 5), 1u << (p & 31));
       }
-      __syncthreads();
     }
-#pragma unroll
-    for (int k = 0; k < kHalf; ++k) park[k * kFusedThreads + tid] = tmp[k];
-#pragma unroll
-    for (int k = 0; k < kRest; ++k) tmp[k] = load_chunk((kHalf + k) * kFusedThreads + tid);
-#pragma unroll
-    for (int k = 0; k < kRest; ++k) park[(kHalf + k) * kFusedThreads + tid] = tmp[k];
+    if (with_isd) __syncthreads();  // mask complete
   }
   // peaks over all samples and over those no impulse touches (zero padding is neutral; NaN propagates like numpy's amax)
   float m_all = 0.f, m_unt = 0.f;
@@ -295,10 +300,7 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
       }
     }
   };
-#pragma unroll
-  for (int k = 0; k < kParkSmem; ++k) peak_chunk(park[k * kFusedThreads + tid], k * kFusedThreads + tid);
-#pragma unroll
-  for (int k = 0; k < kParkRegs; ++k) peak_chunk(keep[k], (kParkSmem + k) * kFusedThreads + tid);
+  // the chunks that do not fit on chip first: their round trips overlap the cp.async traffic of the parked ones
   for (int c0 = kParkChunks + tid; c0 < nchunk; c0 += kOverU * kFusedThreads) {  // chunks that do not fit on chip
     float4 v[kOverU];
 #pragma unroll
@@ -306,6 +308,12 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
 #pragma unroll
     for (int k = 0; k < kOverU; ++k) peak_chunk(v[k], c0 + k * kFusedThreads);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kParkSmem; ++k) peak_chunk(park[k * kFusedThreads + tid], k * kFusedThreads + tid);
+#pragma unroll
+  for (int k = 0; k < kParkRegs; ++k) peak_chunk(keep[k], (kParkSmem + k) * kFusedThreads + tid);
   if (nan_all) m_all = NAN;
   if (nan_unt) m_unt = NAN;
 #pragma unroll
