@@ -280,3 +280,51 @@ def test_workload_matches_oracle_workload():
             assert np.array_equal(workload.synth_utterance(u, 5000, loud), orc.synth_utterance(u, 5000, loud))
         assert workload.seed_for(u) == orc.seed_for(u)
     assert vars(workload.default_args()) == vars(orc.make_args())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# property sweep: the native planner against numpy itself over random arguments, lengths, algos and seeds
+# ---------------------------------------------------------------------------------------------------------
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@st.composite
+def _planner_cases(draw):
+    min_c = draw(st.integers(2, 40))
+    args = orc.make_args(
+        N_f=draw(st.integers(1, 6)), nBands=draw(st.integers(1, 6)),
+        minF=draw(st.integers(1, 400)), maxF=draw(st.integers(2000, 8000)),
+        minBW=draw(st.integers(20, 200)), maxBW=draw(st.integers(300, 1500)),
+        minCoeff=min_c, maxCoeff=min_c + draw(st.integers(1, 120)),
+        minG=draw(st.integers(-6, 3)), maxG=draw(st.integers(-6, 3)),          # low > high is legal (RawBoost.py:62-64)
+        minBiasLinNonLin=draw(st.integers(0, 8)), maxBiasLinNonLin=draw(st.integers(0, 25)),
+        P=draw(st.integers(0, 40)), g_sd=draw(st.integers(1, 4)),
+        SNRmin=draw(st.integers(0, 20)), SNRmax=draw(st.integers(20, 45)))
+    algo = draw(st.integers(1, 8))
+    lens = draw(st.lists(st.integers(1, 3000), min_size=1, max_size=3))
+    seed = draw(st.integers(0, 2 ** 32 - 1))
+    sr = draw(st.sampled_from([16000, 8000, 22050]))
+    if args.maxF >= sr // 2:
+        args.maxF = sr // 2 - 1
+    return args, algo, lens, seed, sr
+
+
+@settings(max_examples=40, deadline=None)
+@given(_planner_cases())
+def test_native_planner_property_sweep(case):
+    """Seeded and global-stream drawing equal numpy's draws (integers and stream state bit for bit) for arbitrary knobs."""
+    from scl_deepfake_audio_detection_b200 import plans as P
+    from scl_deepfake_audio_detection_b200.native_planner import NativePlanner
+    args, algo, lens, seed, sr = case
+    native = NativePlanner(threads=2, pinned=False)
+    seeds = [(seed + 7919 * u) % 2 ** 32 for u in range(len(lens))]
+    _same_plan(native.draw(lens, sr, args, algo, seeds=seeds, copy=True), P.draw_batch(lens, sr, args, algo, seeds=seeds))
+    np.random.seed(seed)
+    ref = P.draw_batch(lens, sr, args, algo)
+    ref_state = np.random.get_state()
+    np.random.seed(seed)
+    got = native.draw(lens, sr, args, algo, use_global_stream=True, copy=True)
+    got_state = np.random.get_state()
+    _same_plan(got, ref)
+    assert np.array_equal(ref_state[1], got_state[1]) and ref_state[2:] == got_state[2:]
