@@ -33,6 +33,32 @@ __all__ = [
 ]
 
 _DEVICE = int(os.environ.get("RAWBOOST_B200_DEVICE", "0"))
+# Who issues the draws of the dispatcher: "native" (default) = the library's bit-exact C++ replica of the numpy calls, run
+# on numpy's own global stream state (about 7x faster than numpy + scipy per utterance; integers, impulse gains, noise and the
+# stream state after the call are identical, taps agree to ~1e-15 before the float32 cast); "numpy" = the numpy / scipy calls
+# themselves (plans.py).
+_PLANNER = os.environ.get("RAWBOOST_B200_PLANNER", "native")
+_native = None
+
+
+_ZERO_ARGS = dict(N_f=1, nBands=1, minF=0, maxF=0, minBW=0, maxBW=0, minCoeff=0, maxCoeff=0, minG=0, maxG=0, minBiasLinNonLin=0,
+                  maxBiasLinNonLin=0, P=0, g_sd=0, SNRmin=0, SNRmax=0)
+
+
+def _draw_native(length, fs, algo, **knobs):
+    """One operator's draws by the native planner on numpy's global stream (only the knobs the operator reads matter)."""
+    from types import SimpleNamespace
+    kw = dict(_ZERO_ARGS)
+    kw.update(knobs)
+    return _native_planner().draw([length], fs, SimpleNamespace(**kw), algo, use_global_stream=True)
+
+
+def _native_planner():
+    global _native
+    if _native is None:
+        from .native_planner import NativePlanner
+        _native = NativePlanner(threads=1, pinned=False)
+    return _native
 
 
 def _as_wave(x):
@@ -43,13 +69,14 @@ def _as_wave(x):
 
 
 def _run_single(algo, x, plan):
-    """One utterance through ``rb_process``: returns a new float32 array of x's length."""
+    """One utterance through ``rb_process``: returns a new float32 array of x's length. ``plan``: an ``UtterancePlan`` or an
+    already packed one-utterance ``BatchPlan``."""
     eng = default_engine(_DEVICE)
     n = x.shape[0]
     if n == 0:
         return np.zeros(0, dtype=np.float32)
     xd, ld = eng.pack_waveforms([x])
-    bp = _plans.pack([plan]) if plan is not None else None
+    bp = plan if isinstance(plan, _plans.BatchPlan) else (_plans.pack([plan]) if plan is not None else None)
     dp = eng.upload_plan(bp) if bp is not None else None
     y = eng.process(algo, xd, ld, dp)
     return y[0, :n].cpu().numpy()
@@ -85,6 +112,10 @@ def LnL_convolutive_noise(x, N_f, nBands, minF, maxF, minBW, maxBW, minCoeff, ma
                           maxBiasLinNonLin, fs):
     """Linear and non-linear convolutive noise (RawBoost.py:59-69)."""
     x = _as_wave(x)
+    if _PLANNER == "native" and x.shape[0] > 0:
+        return _run_single(1, x, _draw_native(x.shape[0], fs, 1, N_f=N_f, nBands=nBands, minF=minF, maxF=maxF, minBW=minBW, maxBW=maxBW,
+                                              minCoeff=minCoeff, maxCoeff=maxCoeff, minG=minG, maxG=maxG,
+                                              minBiasLinNonLin=minBiasLinNonLin, maxBiasLinNonLin=maxBiasLinNonLin))
     plan = _plans.UtterancePlan(length=x.shape[0])
     plan.lnl_taps = _plans.draw_lnl(N_f, nBands, minF, maxF, minBW, maxBW, minCoeff, maxCoeff, minG, maxG, minBiasLinNonLin,
                                     maxBiasLinNonLin, fs)
@@ -94,6 +125,8 @@ def LnL_convolutive_noise(x, N_f, nBands, minF, maxF, minBW, maxBW, minCoeff, ma
 def ISD_additive_noise(x, P, g_sd):
     """Impulsive signal-dependent noise (RawBoost.py:73-84)."""
     x = _as_wave(x)
+    if _PLANNER == "native" and x.shape[0] > 0:
+        return _run_single(2, x, _draw_native(x.shape[0], 16000, 2, P=P, g_sd=g_sd))
     plan = _plans.UtterancePlan(length=x.shape[0])
     plan.isd_idx, plan.isd_fr = _plans.draw_isd(x.shape[0], P)
     plan.g_sd = float(g_sd)
@@ -103,6 +136,9 @@ def ISD_additive_noise(x, P, g_sd):
 def SSI_additive_noise(x, SNRmin, SNRmax, nBands, minF, maxF, minBW, maxBW, minCoeff, maxCoeff, minG, maxG, fs):
     """Stationary signal-independent coloured noise (RawBoost.py:89-97)."""
     x = _as_wave(x)
+    if _PLANNER == "native" and x.shape[0] > 0:
+        return _run_single(3, x, _draw_native(x.shape[0], fs, 3, SNRmin=SNRmin, SNRmax=SNRmax, nBands=nBands, minF=minF, maxF=maxF,
+                                              minBW=minBW, maxBW=maxBW, minCoeff=minCoeff, maxCoeff=maxCoeff, minG=minG, maxG=maxG))
     plan = _plans.UtterancePlan(length=x.shape[0])
     plan.ssi_noise, plan.ssi_taps, plan.ssi_snr_db = _plans.draw_ssi(x.shape[0], SNRmin, SNRmax, nBands, minF, maxF, minBW, maxBW,
                                                                      minCoeff, maxCoeff, minG, maxG, fs)
@@ -117,7 +153,10 @@ def process_Rawboost_feature(feature, sr, args, algo):
     if algo not in (1, 2, 3, 4, 5, 6, 7, 8):
         return feature
     x = _as_wave(feature)
-    plan = _plans.draw_for_algo(x.shape[0], sr, args, algo)
+    if _PLANNER == "native" and x.shape[0] > 0:
+        plan = _native_planner().draw([x.shape[0]], sr, args, algo, use_global_stream=True)
+    else:
+        plan = _plans.draw_for_algo(x.shape[0], sr, args, algo)
     return _run_single(algo, x, plan)
 
 
