@@ -343,6 +343,32 @@ def gpu_arm(a):
         sharding.barrier()
         return dt / steps
 
+    y_host2 = torch.empty((B, ld), dtype=torch.float32).pin_memory() if a.planner == "device" and not a.no_e2e else None
+    lengths_i32 = np.ascontiguousarray(bp.lengths, dtype=np.int32)
+
+    def e2e_run_stream(steps, warm):
+        """The streaming form a production loader uses: rb_submit_host_seeded / rb_ctx_wait with two calls in flight and two
+        result buffers -- step k's results are collected while step k+1 is already being copied in. Every step still moves
+        its waveforms host -> device and its results device -> host inside the timed region."""
+        bufs = (y_host.numpy(), y_host2.numpy())
+
+        def run(n):
+            prev = None
+            for k in range(n):
+                t = eng.submit_host_seeded(algo, x_host.numpy(), lengths_i32, seeds_np, workload.SAMPLE_RATE, args, out=bufs[k % 2])
+                if prev is not None:
+                    eng.wait_host(prev)
+                prev = t
+            eng.wait_host(prev)
+
+        run(warm)
+        sharding.barrier()
+        t0 = time.perf_counter()
+        run(steps)
+        dt = time.perf_counter() - t0
+        sharding.barrier()
+        return dt / steps
+
     def e2e_run(steps, warm):
         if a.planner == "device":
             return e2e_run_device(steps, warm)
@@ -377,9 +403,14 @@ def gpu_arm(a):
     if a.no_e2e:
         e2e_s, copy_s, h2d, d2h, check = float("nan"), float("nan"), 0, 0, None
     else:
-        e2e_s = sharding.max_over_ranks(e2e_run(e2e_steps, 2), dev)
+        sync_s = sharding.max_over_ranks(e2e_run(e2e_steps, 2), dev)   # one blocking call per step
         h2d, d2h = eng.last_host_traffic()
         e2e_check = y_host.numpy()[:, :L].copy() if a.planner == "device" else None
+        e2e_s = sync_s
+        if a.planner == "device":
+            e2e_s = sharding.max_over_ranks(e2e_run_stream(e2e_steps, 2), dev)
+            assert np.array_equal(y_host.numpy()[:, :L], e2e_check) and np.array_equal(y_host2.numpy()[:, :L], e2e_check), \
+                "streamed results differ from the blocking call's"
         # copy + kernels only (plans pre-drawn), for the breakdown
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -431,15 +462,18 @@ def gpu_arm(a):
                        "step_ms_min_max": [min(step_ms), max(step_ms)], "plan_draw_s_setup": t_plan, "host_plan_workers": workers},
             "roofline": roofline,
             "e2e": {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "includes": ("H2D of waveforms + seeds, plan draw ON THE DEVICE (bit-exact replay of numpy's MT19937 stream, "
-                                 "rb_devplan_draw), kernels, D2H; chunked 3-stage pipeline through rb_process_host_seeded"
+                    "includes": ("every step: H2D of its waveforms + seeds from pinned host memory, plan draw ON THE DEVICE (bit-exact "
+                                 "replay of numpy's MT19937 stream), kernels, D2H of its results into pinned host memory; streaming "
+                                 "API rb_submit_host_seeded / rb_ctx_wait with two calls in flight (results of step k collected "
+                                 "while step k+1 is copied in); blocking_call_* = one rb_process_host_seeded call per step"
                                  if a.planner == "device" else
                                  "host plan draw (%s, %d host %s, overlapped with the previous step) + H2D + kernels + D2H"
                                  % (("native planner: bit-exact numpy MT19937 stream + float64 filter design", workers, "threads")
                                     if native else ("numpy/scipy", workers, "processes"))),
                     "planner": a.planner,
                     "plan_draw_s_per_batch": t_plan,
-                    "ms_per_step": e2e_s * 1e3, "copy_and_kernels_only_ms_per_step": copy_s * 1e3,
+                    "ms_per_step": e2e_s * 1e3, "blocking_call_ms_per_step": sync_s * 1e3,
+                    "blocking_call_value": world * B / sync_s, "copy_and_kernels_only_ms_per_step": copy_s * 1e3,
                     "copy_and_kernels_only_value": world * B / copy_s, "steps": e2e_steps, "result_check_max_abs": check},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -489,7 +523,7 @@ def main():
     ap.add_argument("--algo", type=int, default=5, help="RawBoost algo (BASELINE config 3: algo 5 = LnL -> ISD)")
     ap.add_argument("--batch", type=int, default=4096, help="utterances per GPU per step (BASELINE config 3: 4096)")
     ap.add_argument("--length", type=int, default=64600)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--planner", choices=["device", "native", "numpy"], default="device",
                     help="plan drawing in the e2e leg: on the device from per-utterance seeds (default), the native host "
                          "re-implementation, or the numpy calls themselves")

@@ -209,6 +209,14 @@ RB_API int rb_process_host_seeded(rb_ctx* ctx, int algo, const rb_args* args, co
 RB_API int rb_multiview_assemble(const float* views, const int32_t* len, int G, int V, int ld, const int32_t* start, int length,
                                  int repeat_pad, int layout, float* out, int32_t* out_len, void* stream);
 
+/* Streaming form of rb_process_host_seeded: queues the whole call and returns at once; *ticket identifies it. Up to two calls
+ * may be in flight (a third submit first waits for the oldest), so the copies of consecutive batches follow each other
+ * without a gap and steady-state throughput is bound by PCIe alone. x, len, seeds and y must stay valid -- and y must not
+ * be read -- until rb_ctx_wait(ctx, ticket) has returned (ticket 0 waits for everything submitted so far). */
+RB_API int rb_submit_host_seeded(rb_ctx* ctx, int algo, const rb_args* args, const float* x, const int32_t* len,
+                                 const uint32_t* seeds, int B, int ld, float* y, uint64_t* ticket);
+RB_API int rb_ctx_wait(rb_ctx* ctx, uint64_t ticket);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------------------
  * rb_probe_fp32: runs a register-resident FFMA2 (packed=1) or FFMA (packed=0) chain on every SM and
  * returns the achieved FLOP count in *flops; the caller times it with events on `stream`.

@@ -337,19 +337,28 @@ struct Slot {
 };
 }  // namespace
 
+// Resources one call owns while it is in flight; two sets, so that a second call can be submitted while the first drains.
+struct CallRes {
+  char* meta = nullptr;  // device copy of len[] and seeds[]
+  size_t meta_bytes = 0;
+  char* planmem = nullptr;  // device-drawn plans of the whole batch (rb_process_host_seeded)
+  size_t planmem_bytes = 0;
+  std::vector<cudaEvent_t> ev_planned;  // one per chunk
+  cudaEvent_t ev_meta = nullptr, ev_body[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr;
+  bool inflight = false;
+  uint64_t ticket = 0;
+};
+
 struct rb_ctx {
   int device;
   int sm_count;
   int chunk;  // utterances per pipeline chunk (0: four per SM)
   int plan_mode;  // device planner: 0 = on its own streams beside the kernels (default), 1 = in line on the kernels' stream
   cudaStream_t s_in, s_plan, s_apply, s_cmp, s_out;
-  cudaEvent_t ev_meta, ev_body[3];
   Slot slot[kSlots];
-  char* meta = nullptr;  // per-call device copy of len[] and seeds[]
-  size_t meta_bytes = 0;
-  char* planmem = nullptr;  // device-drawn plans of the whole batch (rb_process_host_seeded)
-  size_t planmem_bytes = 0;
-  std::vector<cudaEvent_t> ev_planned;  // one per chunk
+  uint64_t seq = 0;    // chunks issued so far (slot = seq % kSlots)
+  uint64_t calls = 0;  // calls issued so far (resources = calls % 2)
+  CallRes res[2];
   uint64_t h2d, d2h;
   int trace = 0;                 // rb_ctx_trace: record a per-chunk timeline of the next calls
   std::vector<double> timeline;  // per chunk: first utterance, utterances, ms at which copy-in / plan / kernels / copy-out ended
@@ -379,8 +388,13 @@ struct Take {
 
 // Common driver. plan != NULL: host CSR plan, sliced and uploaded per chunk. plan == NULL: seeds/args given, drawn on the device.
 int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, const rb_args* args,
-                 const uint32_t* seeds, float* y) {
+                 const uint32_t* seeds, float* y, bool async, uint64_t* ticket) {
   RB_CUDA(cudaSetDevice(c->device));
+  CallRes& R = c->res[c->calls & 1];
+  if (R.inflight) {  // at most two calls in flight: the one that used this resource set must be complete
+    RB_CUDA(cudaEventSynchronize(R.ev_done));
+    R.inflight = false;
+  }
   const bool active = algo >= 1 && algo <= 8;
   const bool use_lnl = (algo == 1 || algo == 4 || algo == 5 || algo == 6 || algo == 8);
   const bool use_isd = (algo == 2 || algo == 4 || algo == 5 || algo == 7 || algo == 8);
@@ -405,16 +419,16 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
   // everything queued below is ordered by events only; the host blocks once, at the end
   // per-call metadata: lengths (+ seeds) for the whole batch
   const size_t meta_need = align_up((size_t)B * 4, 256) * 2;
-  if (meta_need > c->meta_bytes) {
+  if (meta_need > R.meta_bytes) {
     RB_CUDA(cudaDeviceSynchronize());
-    if (c->meta) RB_CUDA(cudaFree(c->meta));
-    c->meta = nullptr;
-    c->meta_bytes = 0;
-    RB_CUDA(cudaMalloc((void**)&c->meta, meta_need));
-    c->meta_bytes = meta_need;
+    if (R.meta) RB_CUDA(cudaFree(R.meta));
+    R.meta = nullptr;
+    R.meta_bytes = 0;
+    RB_CUDA(cudaMalloc((void**)&R.meta, meta_need));
+    R.meta_bytes = meta_need;
   }
-  int32_t* d_len = (int32_t*)c->meta;
-  uint32_t* d_seeds = (uint32_t*)(c->meta + align_up((size_t)B * 4, 256));
+  int32_t* d_len = (int32_t*)R.meta;
+  uint32_t* d_seeds = (uint32_t*)(R.meta + align_up((size_t)B * 4, 256));
   uint64_t h2d = 0, d2h = 0;
   RB_CUDA(cudaMemcpyAsync(d_len, len, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
   h2d += (size_t)B * 4;
@@ -422,27 +436,27 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     RB_CUDA(cudaMemcpyAsync(d_seeds, seeds, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
     h2d += (size_t)B * 4;
   }
-  RB_CUDA(cudaEventRecord(c->ev_meta, c->s_in));
-  RB_CUDA(cudaStreamWaitEvent(c->s_plan, c->ev_meta, 0));
-  RB_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_meta, 0));
+  RB_CUDA(cudaEventRecord(R.ev_meta, c->s_in));
+  RB_CUDA(cudaStreamWaitEvent(c->s_plan, R.ev_meta, 0));
+  RB_CUDA(cudaStreamWaitEvent(c->s_cmp, R.ev_meta, 0));
 
   // slot layout for the largest chunk
   const size_t wave = (size_t)chunk * ld * sizeof(float);
   const size_t ws_bytes = active ? rb_workspace_bytes_for(algo, chunk, ld) : 0;
   const size_t dp_bytes = devplan ? rb_devplan_bytes(args, algo, B, ld) : 0;
   if (devplan && dp_bytes == 0) return RB_ERR_UNSUPPORTED;
-  if (dp_bytes > c->planmem_bytes) {
+  if (dp_bytes > R.planmem_bytes) {
     RB_CUDA(cudaDeviceSynchronize());
-    if (c->planmem) RB_CUDA(cudaFree(c->planmem));
-    c->planmem = nullptr;
-    c->planmem_bytes = 0;
-    RB_CUDA(cudaMalloc((void**)&c->planmem, dp_bytes + dp_bytes / 8));
-    c->planmem_bytes = dp_bytes + dp_bytes / 8;
+    if (R.planmem) RB_CUDA(cudaFree(R.planmem));
+    R.planmem = nullptr;
+    R.planmem_bytes = 0;
+    RB_CUDA(cudaMalloc((void**)&R.planmem, dp_bytes + dp_bytes / 8));
+    R.planmem_bytes = dp_bytes + dp_bytes / 8;
   }
-  while (devplan && (int)c->ev_planned.size() < nchunks) {
+  while (devplan && (int)R.ev_planned.size() < nchunks) {
     cudaEvent_t e;
     RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    c->ev_planned.push_back(e);
+    R.ev_planned.push_back(e);
   }
   size_t max_lt = 0, max_isd = 0, max_st = 0;  // largest per-chunk CSR payloads of a host plan
   if (active && !devplan) {
@@ -460,15 +474,16 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
   const size_t o_sn = take(use_ssi && !devplan ? wave : 0), o_so = take(use_ssi && !devplan ? (size_t)(chunk + 1) * 4 : 0),
                o_st = take(max_st * 4), o_sr = take(use_ssi && !devplan ? (size_t)chunk * 4 : 0);
   for (int k = 0; k < std::min(kSlots, nchunks); ++k) {
-    if (take.off > c->slot[k].bytes) {
+    Slot& sl = c->slot[(c->seq + k) % kSlots];
+    if (take.off > sl.bytes) {
       RB_CUDA(cudaDeviceSynchronize());
-      RB_TRY(slot_reserve(c->slot[k], take.off));
+      RB_TRY(slot_reserve(sl, take.off));
     }
   }
 
   std::vector<cudaEvent_t> tev[5];  // trace: [0] start of the call, [1..4] per chunk: copy-in, plan, kernels, copy-out
   auto mark = [&](int stage, cudaStream_t st) {
-    if (!c->trace) return;
+    if (!c->trace || async) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) == cudaSuccess) {
       cudaEventRecord(e, st);
@@ -493,15 +508,15 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
   auto plan_piece = [&](int pc, cudaStream_t s_body, cudaStream_t s_swap) -> int {
     const int cb = pc ? piece_end[pc - 1] : 0;
     const int u0 = first[cb], u1 = first[piece_end[pc]];
-    RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, c->planmem, u0, u1 - u0, s_body));
-    if (use_ssi) RB_TRY(devplan_end(args, algo, B, ld, c->planmem, s_body));
+    RB_TRY(devplan_body(args, algo, B, ld, d_len, d_seeds, R.planmem, u0, u1 - u0, s_body));
+    if (use_ssi) RB_TRY(devplan_end(args, algo, B, ld, R.planmem, s_body));
     if (s_swap != s_body) {
-      RB_CUDA(cudaEventRecord(c->ev_body[pc], s_body));
-      RB_CUDA(cudaStreamWaitEvent(s_swap, c->ev_body[pc], 0));
+      RB_CUDA(cudaEventRecord(R.ev_body[pc], s_body));
+      RB_CUDA(cudaStreamWaitEvent(s_swap, R.ev_body[pc], 0));
     }
     for (int ci = cb; ci < piece_end[pc]; ++ci) {
-      RB_TRY(devplan_apply(args, algo, B, ld, d_len, c->planmem, first[ci], first[ci + 1] - first[ci], s_swap));
-      if (s_swap != c->s_cmp) RB_CUDA(cudaEventRecord(c->ev_planned[ci], s_swap));
+      RB_TRY(devplan_apply(args, algo, B, ld, d_len, R.planmem, first[ci], first[ci + 1] - first[ci], s_swap));
+      if (s_swap != c->s_cmp) RB_CUDA(cudaEventRecord(R.ev_planned[ci], s_swap));
       mark(2, s_swap);
     }
     return RB_OK;
@@ -510,17 +525,17 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
   memset(&whole, 0, sizeof(whole));
   if (devplan) {
     const cudaStream_t s0 = c->plan_mode ? c->s_cmp : c->s_plan;
-    RB_TRY(devplan_begin(args, algo, B, ld, d_len, d_seeds, c->planmem, c->planmem_bytes, &whole, s0));
+    RB_TRY(devplan_begin(args, algo, B, ld, d_len, d_seeds, R.planmem, R.planmem_bytes, &whole, s0));
     if (!c->plan_mode)
       for (int pc = 0; pc < npieces; ++pc) RB_TRY(plan_piece(pc, c->s_plan, c->s_apply));
   }
   for (int ci = 0; ci < nchunks; ++ci) {
-    Slot& sl = c->slot[ci % kSlots];
+    Slot& sl = c->slot[(c->seq + ci) % kSlots];
     char* d = sl.dev;
     const int u0 = first[ci], bc = first[ci + 1] - u0;
     const size_t cw = (size_t)bc * ld * sizeof(float);
     // ---- stage 1: host -> device ------------------------------------------------------------------------------------
-    if (ci >= kSlots) RB_CUDA(cudaStreamWaitEvent(c->s_in, sl.ev_out, 0));  // the slot's previous chunk has left the device
+    if (c->seq + ci >= kSlots) RB_CUDA(cudaStreamWaitEvent(c->s_in, sl.ev_out, 0));  // the slot's previous chunk has left the device
     RB_CUDA(cudaMemcpyAsync(d + o_x, x + (size_t)u0 * ld, cw, cudaMemcpyHostToDevice, c->s_in));
     h2d += cw;
     rb_plan dp;
@@ -581,7 +596,7 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
         for (int pc = 0; pc < npieces; ++pc)
           if (ci == (pc ? piece_end[pc - 1] : 0)) RB_TRY(plan_piece(pc, c->s_cmp, c->s_cmp));
       } else {
-        RB_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_planned[ci], 0));
+        RB_CUDA(cudaStreamWaitEvent(c->s_cmp, R.ev_planned[ci], 0));
       }
     }
     if (!devplan) mark(2, c->s_in);
@@ -597,7 +612,16 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     RB_CUDA(cudaEventRecord(sl.ev_out, c->s_out));
     mark(4, c->s_out);
   }
-  RB_CUDA(cudaStreamSynchronize(c->s_out));
+  c->seq += (uint64_t)nchunks;
+  RB_CUDA(cudaEventRecord(R.ev_done, c->s_out));
+  R.inflight = true;
+  R.ticket = ++c->calls;
+  if (ticket) *ticket = R.ticket;
+  c->h2d = h2d;
+  c->d2h = d2h;
+  if (async) return RB_OK;  // the caller collects the results with rb_ctx_wait
+  RB_CUDA(cudaEventSynchronize(R.ev_done));
+  R.inflight = false;
   if (c->trace) {
     c->timeline.clear();
     RB_CUDA(cudaDeviceSynchronize());
@@ -642,8 +666,6 @@ int rb_ctx_create(rb_ctx** out, int device) {
   c->plan_mode = 0;
   c->h2d = c->d2h = 0;
   c->s_in = c->s_plan = c->s_apply = c->s_cmp = c->s_out = nullptr;
-  c->ev_meta = nullptr;
-  for (cudaEvent_t& e : c->ev_body) e = nullptr;
   // Stream priorities: copies first, then the FIR kernel's stream, the planner's streams last. The planner only needs to stay
   // ahead of the filtering (it is ~2.5x faster per chunk), so it runs in the gaps -- while the filtering waits for the next
   // chunk's waveforms, and in whatever an SM has left beside the FIR-bank CTAs -- instead of displacing them: measured 27.3 ms
@@ -654,9 +676,9 @@ int rb_ctx_create(rb_ctx** out, int device) {
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_hi);
   for (cudaStream_t* s : {&c->s_plan, &c->s_apply})
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_lo);
-  for (cudaEvent_t& ev : c->ev_body)
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_meta, cudaEventDisableTiming);
+  for (CallRes& R : c->res)
+    for (cudaEvent_t* ev : {&R.ev_meta, &R.ev_body[0], &R.ev_body[1], &R.ev_body[2], &R.ev_done})
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   for (Slot& sl : c->slot)
     for (cudaEvent_t* ev : {&sl.ev_in, &sl.ev_planned, &sl.ev_done, &sl.ev_out})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -677,12 +699,13 @@ int rb_ctx_destroy(rb_ctx* c) {
     for (cudaEvent_t ev : {sl.ev_in, sl.ev_planned, sl.ev_done, sl.ev_out})
       if (ev) cudaEventDestroy(ev);
   }
-  if (c->meta) cudaFree(c->meta);
-  if (c->planmem) cudaFree(c->planmem);
-  for (cudaEvent_t e : c->ev_planned) cudaEventDestroy(e);
-  if (c->ev_meta) cudaEventDestroy(c->ev_meta);
-  for (cudaEvent_t e : c->ev_body)
-    if (e) cudaEventDestroy(e);
+  for (CallRes& R : c->res) {
+    if (R.meta) cudaFree(R.meta);
+    if (R.planmem) cudaFree(R.planmem);
+    for (cudaEvent_t e : R.ev_planned) cudaEventDestroy(e);
+    for (cudaEvent_t e : {R.ev_meta, R.ev_body[0], R.ev_body[1], R.ev_body[2], R.ev_done})
+      if (e) cudaEventDestroy(e);
+  }
   for (cudaStream_t s : {c->s_in, c->s_plan, c->s_apply, c->s_cmp, c->s_out})
     if (s) cudaStreamDestroy(s);
   delete c;
@@ -734,7 +757,7 @@ int rb_process_host(rb_ctx* c, int algo, const float* x, const int32_t* len, int
   RB_TRY(check_host_batch(c, x, len, B, ld, y));
   if (B == 0 || ld == 0) return RB_OK;
   if (algo >= 1 && algo <= 8 && !plan) return RB_ERR_PLAN;
-  return run_pipeline(c, algo, x, len, B, ld, plan, nullptr, nullptr, y);
+  return run_pipeline(c, algo, x, len, B, ld, plan, nullptr, nullptr, y, false, nullptr);
 }
 
 int rb_process_host_seeded(rb_ctx* c, int algo, const rb_args* args, const float* x, const int32_t* len, const uint32_t* seeds, int B,
@@ -742,7 +765,28 @@ int rb_process_host_seeded(rb_ctx* c, int algo, const rb_args* args, const float
   RB_TRY(check_host_batch(c, x, len, B, ld, y));
   if (B == 0 || ld == 0) return RB_OK;
   if (algo >= 1 && algo <= 8 && (!args || !seeds)) return RB_ERR_INVALID_ARG;
-  return run_pipeline(c, algo, x, len, B, ld, nullptr, args, seeds, y);
+  return run_pipeline(c, algo, x, len, B, ld, nullptr, args, seeds, y, false, nullptr);
+}
+
+int rb_submit_host_seeded(rb_ctx* c, int algo, const rb_args* args, const float* x, const int32_t* len, const uint32_t* seeds, int B,
+                          int ld, float* y, uint64_t* ticket) {
+  if (ticket) *ticket = 0;
+  RB_TRY(check_host_batch(c, x, len, B, ld, y));
+  if (B == 0 || ld == 0) return RB_OK;
+  if (algo >= 1 && algo <= 8 && (!args || !seeds)) return RB_ERR_INVALID_ARG;
+  return run_pipeline(c, algo, x, len, B, ld, nullptr, args, seeds, y, true, ticket);
+}
+
+int rb_ctx_wait(rb_ctx* c, uint64_t ticket) {
+  if (!c) return RB_ERR_INVALID_ARG;
+  RB_CUDA(cudaSetDevice(c->device));
+  for (CallRes& R : c->res) {
+    if (R.inflight && (ticket == 0 || R.ticket <= ticket)) {  // 0: everything submitted so far
+      RB_CUDA(cudaEventSynchronize(R.ev_done));
+      R.inflight = false;
+    }
+  }
+  return RB_OK;
 }
 
 }  // extern "C"

@@ -246,6 +246,27 @@ class Engine:
         _lib.check(rc, f"rb_process_host_seeded(algo={algo})")
         return out
 
+    def submit_host_seeded(self, algo: int, x: np.ndarray, lengths: np.ndarray, seeds: np.ndarray, sr, args, out: np.ndarray) -> int:
+        """Streaming form of :meth:`process_host_seeded`: queue the call and return a ticket at once. Up to two calls may be in
+        flight; ``x``, ``lengths``, ``seeds`` and ``out`` (contiguous, ideally page-locked, of the exact dtypes int32 / uint32 /
+        float32) must stay alive and untouched until :meth:`wait_host` has returned for the ticket."""
+        if x.dtype != np.float32 or x.ndim != 2 or not x.flags.c_contiguous or out.dtype != np.float32 or out.shape != x.shape:
+            raise ValueError("x / out must be C-contiguous [B, ld] float32 arrays of the same shape")
+        if lengths.dtype != np.int32 or seeds.dtype != np.uint32 or not lengths.flags.c_contiguous or not seeds.flags.c_contiguous:
+            raise ValueError("lengths must be a contiguous int32 array and seeds a contiguous uint32 array")
+        B, ld = x.shape
+        a = _lib.args_struct(args, sr)
+        ticket = C.c_uint64(0)
+        rc = self.lib.rb_submit_host_seeded(self._host_ctx(), int(algo), C.byref(a), C.c_void_p(x.ctypes.data),
+                                            C.c_void_p(lengths.ctypes.data), C.c_void_p(seeds.ctypes.data), B, ld,
+                                            C.c_void_p(out.ctypes.data), C.byref(ticket))
+        _lib.check(rc, f"rb_submit_host_seeded(algo={algo})")
+        return int(ticket.value)
+
+    def wait_host(self, ticket: int = 0) -> None:
+        """Block until the submitted call ``ticket`` (0: every submitted call) has delivered its results."""
+        _lib.check(self.lib.rb_ctx_wait(self._host_ctx(), int(ticket)), "rb_ctx_wait")
+
     def trace_host(self, on: bool) -> None:
         """Record a per-chunk timeline of the following host-buffer calls (see :meth:`host_timeline`)."""
         _lib.check(self.lib.rb_ctx_trace(self._host_ctx(), int(bool(on))), "rb_ctx_trace")

@@ -177,3 +177,34 @@ def test_device_plan_many_seeds_full_length(eng, P):
     for u in range(0, B, 37):
         idx = got.isd_idx[got.isd_off[u]:got.isd_off[u + 1]]
         assert idx.min(initial=0) >= 0 and idx.max(initial=0) < 64600 and np.unique(idx).size == idx.size
+
+
+def test_streaming_submit_wait_equals_blocking_calls(eng):
+    """rb_submit_host_seeded / rb_ctx_wait with two calls in flight deliver exactly what the blocking call delivers."""
+    rs = np.random.RandomState(17)
+    lengths = np.array([64600, 3000, 41234, 64600, 7, 20000], np.int32)
+    ld = 64600
+    xs = []
+    for k in range(4):
+        x = np.zeros((len(lengths), ld), np.float32)
+        for u, n in enumerate(lengths):
+            x[u, :n] = (0.4 * rs.standard_normal(n)).astype(np.float32)
+        xs.append(x)
+    seeds = [np.arange(100 * k, 100 * k + len(lengths), dtype=np.uint32) for k in range(4)]
+    eng.set_host_chunk(2)
+    try:
+        ref = [eng.process_host_seeded(5, xs[k], lengths, seeds[k], 16000, ARGS) for k in range(4)]
+        outs = [np.full_like(xs[0], np.nan) for _ in range(4)]
+        tickets = []
+        for k in range(4):
+            tickets.append(eng.submit_host_seeded(5, xs[k], lengths, seeds[k], 16000, ARGS, out=outs[k]))
+            if k >= 1:
+                eng.wait_host(tickets[k - 1])
+                for u, n in enumerate(lengths):
+                    assert np.array_equal(outs[k - 1][u, :n], ref[k - 1][u, :n])
+        eng.wait_host(0)
+        for u, n in enumerate(lengths):
+            assert np.array_equal(outs[3][u, :n], ref[3][u, :n])
+        assert tickets == sorted(tickets) and len(set(tickets)) == 4
+    finally:
+        eng.set_host_chunk(0)
