@@ -401,7 +401,7 @@ def gpu_arm(a):
     if a.host_chunk:
         eng.set_host_chunk(a.host_chunk)
     if a.no_e2e:
-        e2e_s, copy_s, h2d, d2h, check = float("nan"), float("nan"), 0, 0, None
+        e2e_s, sync_s, copy_s, h2d, d2h, check = float("nan"), float("nan"), float("nan"), 0, 0, None
     else:
         sync_s = sharding.max_over_ranks(e2e_run(e2e_steps, 2), dev)   # one blocking call per step
         h2d, d2h = eng.last_host_traffic()

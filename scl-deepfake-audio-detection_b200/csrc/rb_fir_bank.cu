@@ -169,6 +169,9 @@ __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __r
 #ifndef RB_MIN_BLOCKS
 #define RB_MIN_BLOCKS 4
 #endif
+// kTailMode is a compile-time constant: each tail (none / LnL[->ISD] / SSI) is its own kernel, so the code of one never weighs on
+// the register allocation and instruction schedule of another.
+template <int kTailMode>
 __global__ void __launch_bounds__(kThreads, RB_MIN_BLOCKS)
 fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, const float* __restrict__ taps,
                 const int32_t* __restrict__ tap_off, int n_f, int pow_base, int pow_step, float* __restrict__ y,
@@ -317,12 +320,12 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
         if (p + q < valid) yrow[p + q] = sm.xp[p + q];
     }
   }
-  if (tail.mode == TAIL_NONE) return;
+  if (kTailMode == TAIL_NONE) return;
 
   // ---- fused tail: the CTA that finishes the last tile of an utterance finalises the whole utterance -----------------------
   // (per-utterance reductions need every tile, so this is the one grid-level dependency of the path; the raw tiles were
   // written a moment ago and are read back from L2 while the other CTAs of the SM keep the FP32 pipe busy.)
-  if (tail.mode == TAIL_SSI) {  // per-tile sum of squares of the signal the noise is added to
+  if (kTailMode == TAIL_SSI) {  // per-tile sum of squares of the signal the noise is added to
     const float* arow = tail.aux + (size_t)u * ld + tile0;
     float sq = 0.f;
 #pragma unroll
@@ -363,7 +366,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
   float* orow = tail.out + (size_t)u * ld;
   const float* ust = stats + (size_t)u * ntiles * kStatN;
   const int nchunk = (len + 3) >> 2;
-  if (tail.mode == TAIL_AFFINE) {
+  if (kTailMode == TAIL_AFFINE) {
     const bool with_isd = tail.isd_off != nullptr;
     const int ibeg = with_isd ? tail.isd_off[u] : 0, iend = with_isd ? tail.isd_off[u + 1] : 0;
     const UttParams pr = finalize_block(ust, nact, len, 1, 0, raw, tail.isd_idx, tail.isd_fr, ibeg, iend, with_isd, tail.g_sd);
@@ -481,10 +484,12 @@ int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const flo
     const int nb = min(65535, B - b0);
     dim3 grid(ntiles, nb);
     profile_begin(st);
-    fir_bank_kernel<<<grid, kThreads, 0, st>>>(x + (size_t)b0 * ld, len + b0, ld, taps, tap_off + (size_t)b0 * n_f, n_f,
-                                                pow_base, pow_step, y + (size_t)b0 * ld,
-                                                stats ? stats + (size_t)b0 * ntiles * kStatN : nullptr,
-                                                mask ? mask + (size_t)b0 * mask_ld : nullptr, mask_ld, tail.shifted(b0, ld));
+    auto kernel = tail.mode == TAIL_AFFINE ? fir_bank_kernel<TAIL_AFFINE>
+                  : tail.mode == TAIL_SSI  ? fir_bank_kernel<TAIL_SSI>
+                                           : fir_bank_kernel<TAIL_NONE>;
+    kernel<<<grid, kThreads, 0, st>>>(x + (size_t)b0 * ld, len + b0, ld, taps, tap_off + (size_t)b0 * n_f, n_f, pow_base, pow_step,
+                                       y + (size_t)b0 * ld, stats ? stats + (size_t)b0 * ntiles * kStatN : nullptr,
+                                       mask ? mask + (size_t)b0 * mask_ld : nullptr, mask_ld, tail.shifted(b0, ld));
     profile_end(st);
     RB_LAUNCH_CHECK();
   }
