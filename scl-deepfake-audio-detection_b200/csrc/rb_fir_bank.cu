@@ -171,6 +171,9 @@ __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __r
   }
 }
 
+#ifndef RB_UNROLL_LNL
+#define RB_UNROLL_LNL 4
+#endif
 #ifndef RB_MIN_BLOCKS
 #define RB_MIN_BLOCKS 4
 #endif
@@ -254,7 +257,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
         src = sm.xp;
       }
       __syncthreads();
-      if (warp_active) conv_segment<kTailMode == TAIL_AFFINE ? 4 : 2>(acc, src, sm.he, sm.ho, e - z, ngroups);
+      if (warp_active) conv_segment<kTailMode == TAIL_AFFINE ? RB_UNROLL_LNL : 2>(acc, src, sm.he, sm.ho, e - z, ngroups);
     }
   }
   __syncthreads();  // everyone is done reading xp; reuse it to transpose the outputs
