@@ -127,7 +127,7 @@ RB_API int rb_process(int algo, const float* x, const int32_t* len, int B, int l
                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- host-buffer entry points (what a non-torch caller binds; used for the end-to-end measurement) -----
- * A context owns four streams and three device slots on `device`, grown on demand and reused. A batch is cut into
+ * A context owns five streams and eight device slots on `device`, grown on demand and reused. A batch is cut into
  * chunks (default: four utterances per SM, rb_ctx_set_chunk to change) that flow through a three-stage pipeline --
  * host->device copy | plan + kernels | device->host copy -- ordered by events only, so PCIe in both directions and
  * the SMs work at the same time; the call returns when y is complete. Page-locked x / y (and plan arrays) make

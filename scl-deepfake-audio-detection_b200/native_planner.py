@@ -2,7 +2,7 @@
 
 ``lib/librawboost_b200.so`` re-implements, bit for bit, the numpy legacy MT19937 calls the reference makes
 (``/root/reference/datautils/RawBoost.py:15,79,80,90``) and the float64 filter design of ``genNotchCoeffs``
-(RawBoost.py:28-48); see ``csrc/rb_planner.cu``. Tap counts, impulse counts / positions / gains, SSI noise and the stream
+(RawBoost.py:28-48); see ``csrc/rb_planner.cpp``. Tap counts, impulse counts / positions / gains, SSI noise and the stream
 state are identical to numpy's; tap values agree to ~1e-15 relative before the float32 cast. The numpy path in
 :mod:`plans` remains the contract; this is the throughput path (host threads, page-locked output buffers, no GIL).
 """

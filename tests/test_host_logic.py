@@ -209,7 +209,7 @@ def test_two_rank_gloo_sharding(tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# native planner (csrc/rb_planner.cu): bit-exact with the numpy calls of plans.py
+# native planner (csrc/rb_planner.cpp): bit-exact with the numpy calls of plans.py
 # ---------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def native():
