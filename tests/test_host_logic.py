@@ -328,3 +328,12 @@ def test_native_planner_property_sweep(case):
     got_state = np.random.get_state()
     _same_plan(got, ref)
     assert np.array_equal(ref_state[1], got_state[1]) and ref_state[2:] == got_state[2:]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/rawboost_b200.h is the C ABI: it must compile as C (no C++ types in the signatures)."""
+    src = tmp_path / "use.c"
+    src.write_text('#include "rawboost_b200.h"\nint main(void) { rb_plan p; rb_args a; (void)p; (void)a; return RB_ABI_VERSION == 1 ? 0 : 1; }\n')
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
