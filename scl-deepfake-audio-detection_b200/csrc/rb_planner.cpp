@@ -251,12 +251,21 @@ struct Scratch {
   std::vector<double> taps, stage, tmp;
   std::vector<uint32_t> perm;
   std::vector<uint16_t> perm16;
+  std::vector<uint32_t> targets;
+  std::vector<uint16_t> targets16;
 };
 
-// numpy's legacy shuffle of arange(n): for i = n-1 .. 1: j = random_interval(i); swap(x[i], x[j]). The mask only changes
-// when i crosses a power of two, so it is hoisted out of the inner loop.
+// numpy's legacy shuffle of arange(n): for i = n-1 .. 1: j = random_interval(i); swap(x[i], x[j]), in two passes.
+// Pass 1 settles the swap targets: the mask only changes when i crosses a power of two, and inside such a region the
+// rejection loop is branch-free (every masked word is stored, the cursor only advances when it is accepted), so the ~28 % of
+// rejected words cost no mispredicted branches. Pass 2 applies the swaps with the targets known ahead, which lets it
+// prefetch the (cache-missing, 129 KB at 64600 samples) target slots a few steps in advance.
 template <typename T>
-void shuffle_legacy(Mt& rng, T* x, int n) {
+void shuffle_legacy(Mt& rng, T* x, int n, std::vector<T>& js) {  // targets are < n, so they fit the element type
+  if (n < 2) return;
+  js.resize((size_t)n + 1);
+  T* jp = js.data();
+  int k = 0;  // steps settled so far; step k has i = n-1-k
   int i = n - 1;
   while (i >= 1) {
     uint32_t mask = (uint32_t)i;
@@ -266,14 +275,23 @@ void shuffle_legacy(Mt& rng, T* x, int n) {
     mask |= mask >> 8;
     mask |= mask >> 16;
     const int lo = (int)(mask >> 1) + 1;  // smallest i with this mask
-    for (; i >= lo && i >= 1; --i) {
-      uint32_t j;
-      while ((j = (rng.u32() & mask)) > (uint32_t)i) {
-      }
-      const T t = x[j];
-      x[j] = x[i];
-      x[i] = t;
+    while (i >= lo) {
+      const uint32_t v = rng.u32() & mask;
+      jp[k] = (T)v;
+      const int ok = v <= (uint32_t)i;
+      k += ok;
+      i -= ok;
     }
+  }
+  constexpr int kAhead = 12;
+  const int steps = n - 1;
+  for (int s = 0; s < steps; ++s) {
+    if (s + kAhead < steps) __builtin_prefetch(&x[jp[s + kAhead]], 1);
+    const int ii = n - 1 - s;
+    const uint32_t j = jp[s];
+    const T t = x[j];
+    x[j] = x[ii];
+    x[ii] = t;
   }
 }
 
@@ -308,13 +326,13 @@ void draw_utt(Mt& rng, const Args& a, int algo, int length, UttDraw& out, float*
       sc.perm16.resize(length);
       uint16_t* pm = sc.perm16.data();
       for (int i = 0; i < length; ++i) pm[i] = (uint16_t)i;
-      shuffle_legacy(rng, pm, length);
+      shuffle_legacy(rng, pm, length, sc.targets16);
       for (int i = 0; i < n; ++i) out.isd_idx[i] = (int32_t)pm[i];
     } else {
       sc.perm.resize(length);
       uint32_t* pm = sc.perm.data();
       for (int i = 0; i < length; ++i) pm[i] = (uint32_t)i;
-      shuffle_legacy(rng, pm, length);
+      shuffle_legacy(rng, pm, length, sc.targets);
       for (int i = 0; i < n; ++i) out.isd_idx[i] = (int32_t)pm[i];
     }
     for (int i = 0; i < n; ++i) out.isd_fr[i] = 2 * rng.dbl() - 1;
