@@ -165,7 +165,7 @@ int do_isd(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
 }
 
 // SSI: x -> out (out must not alias x: the tail of one utterance reads x while other tiles still compute statistics of it).
-// One FIR-bank launch on the noise; its fused tail takes both norms and adds the scaled coloured noise. buf0 = coloured noise.
+// One FIR-bank launch on the noise (the coloured noise is written into `out`); its fused tail takes both norms and mixes in place.
 int do_ssi(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl, float* out, const Workspace& w, cudaStream_t st) {
   if (!pl || !pl->ssi_noise || !pl->ssi_taps || !pl->ssi_tap_off || !pl->ssi_snr_db) return RB_ERR_PLAN;
   if ((uintptr_t)pl->ssi_noise & 15u) return RB_ERR_ALIGNMENT;

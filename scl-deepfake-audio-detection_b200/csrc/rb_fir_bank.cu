@@ -22,11 +22,16 @@
 //    samples (W[m],W[m+1]), m even. Odd outputs would need misaligned window pairs, so they use a second
 //    copy of the taps shifted by one (ho[i] = he[i-1]) against the same aligned window pairs. The two halves
 //    of an accumulator pair hold the even-tap and odd-tap partial sums of one output and are added at the end.
-//  * Taps are zero-padded to a multiple of 24 (the unrolled body) and reversed so the window slides upwards.
+//  * Taps are reversed so the window slides upwards and zero-padded to whole 4-tap groups: full 24-tap bodies (the loop
+//    is unrolled over two or four of them) are followed by a partial last body that stops after its last useful group.
 //    Filters longer than 512 taps are processed as segments with their own staging offset.
 //  * Epilogue: per-tile sum / sum of squares / min / max (and min / max over samples not hit by an ISD impulse,
 //    from a per-utterance bit mask) via warp shuffles; outputs go through shared memory so the global store is
 //    a coalesced STG.128 stream.
+//  * Fused tail: the CTA that completes the last tile of an utterance (per-utterance arrival counter) does the whole
+//    per-utterance finalisation in place from L2 -- mean removal + normWav [+ ISD scatter + normWav] for LnL, or the
+//    norm-matched mix for SSI -- while the other CTAs of the SM keep the FP32 pipe busy. The kernel is a template over
+//    the tail so that each variant gets its own register allocation and schedule.
 #include "rb_common.cuh"
 #include "rb_finalize.cuh"
 
