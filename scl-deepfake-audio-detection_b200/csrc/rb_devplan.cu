@@ -27,6 +27,8 @@
 //                        the swaps group by group and emits the first n positions
 //   design_kernel        one CTA per filter: windowed-sinc stages, cascade convolution, 1024-point FFT peak, gain, fp32 taps
 #include <math.h>
+
+#include <algorithm>
 #include <string.h>
 
 #include "rb_common.cuh"
@@ -440,10 +442,21 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
+// Phases. Step k swaps slot i = L-1-k with a target j <= i and never looks above i again, so the live part of the array
+// shrinks as the shuffle proceeds. The steps are therefore applied in up to four launches: phase p handles the steps whose
+// slots lie below T_hi (rounded to whole 1024-step staging pieces) and keeps only T_hi entries in shared memory -- 128, 96,
+// 64 and 32 KB -- so that 1, 2, 3 and 6 utterances per SM are in flight instead of one throughout (the kernel is bound by
+// the latency of a single warp per utterance). The array travels between phases through `state` (global, L2-resident);
+// every phase writes back all it holds, so slots finalised in an earlier phase keep their final value there.
+__device__ __forceinline__ int phase_first_step(int L, int T) {  // first step (multiple of 1024) whose slot is below T
+  const int k = L - T;
+  return k <= 0 ? 0 : (k + kStageSteps - 1) / kStageSteps * kStageSteps;
+}
+
 __global__ void __launch_bounds__(32)
 perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uint16_t* __restrict__ jseq_all,
                   const uint32_t* __restrict__ cuts_all, int cuts_ld, const int32_t* __restrict__ isd_off,
-                  int32_t* __restrict__ isd_idx) {
+                  int32_t* __restrict__ isd_idx, uint16_t* __restrict__ state_all, int T_hi, int T_lo) {
   extern __shared__ __align__(16) unsigned char dyn[];
   uint16_t (*jbuf)[kStageSteps] = reinterpret_cast<uint16_t (*)[kStageSteps]>(dyn);                       // [2][1024]
   uint32_t (*cbuf)[kStageSteps / 32] = reinterpret_cast<uint32_t (*)[kStageSteps / 32]>(dyn + 2 * kStageSteps * 2);  // [2][32]
@@ -452,11 +465,16 @@ perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uin
   const int L = len_arr[u];
   const int beg = isd_off[u], n = isd_off[u + 1] - beg;
   if (n <= 0) return;  // no impulse: nothing of the permutation is used
+  const bool last = T_lo <= 0;
+  const int nsteps = max(L - 1, 0);
+  const int kb = min(nsteps, phase_first_step(L, T_hi));                       // steps [kb, ke) belong to this phase
+  const int ke = last ? nsteps : min(nsteps, phase_first_step(L, T_lo));
+  if (kb >= ke && !last) return;  // nothing to do here; the array is created by the first phase that has steps
   const uint16_t* __restrict__ jseq = jseq_all + (size_t)u * jld;
   const uint32_t* __restrict__ cuts = cuts_all + (size_t)u * cuts_ld;
-  const int nsteps = L - 1;
-  const int nchunks = (nsteps + 31) >> 5;
-  const int npieces = (nsteps + kStageSteps - 1) / kStageSteps;
+  uint16_t* __restrict__ state = state_all + (size_t)u * jld;
+  const int live = L - kb;  // slots [0, live) are what this phase can touch (<= T_hi)
+  const int p_begin = kb / kStageSteps, p_end = (ke + kStageSteps - 1) / kStageSteps;
   auto stage = [&](int piece) {  // rows are padded to whole pieces, so no bounds checks
     const uint16_t* src = jseq + (size_t)piece * kStageSteps;
 #pragma unroll
@@ -464,10 +482,20 @@ perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uin
     if (lane < kStageSteps / 32 / 4) cp_async16(&cbuf[piece & 1][lane * 4], cuts + (size_t)piece * (kStageSteps / 32) + lane * 4);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (npieces > 0) stage(0);
-  for (int k = 2 * lane; k < L; k += 64) *reinterpret_cast<uint32_t*>(perm + k) = (uint32_t)k | ((uint32_t)(k + 1) << 16);
-  for (int piece = 0; piece < npieces; ++piece) {
-    if (piece + 1 < npieces) {
+  if (p_begin < p_end) stage(p_begin);
+  if (kb == 0) {  // first phase of this utterance: arange
+    for (int k = 2 * lane; k < live; k += 64) *reinterpret_cast<uint32_t*>(perm + k) = (uint32_t)k | ((uint32_t)(k + 1) << 16);
+  } else {        // the live slots as the previous phase left them: one cp.async group, all of it in flight at once
+    for (int k = 8 * lane; k < live; k += 256) cp_async16(perm + k, state + k);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int nch_end = (ke + 31) >> 5;
+  if (p_begin >= p_end) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  for (int piece = p_begin; piece < p_end; ++piece) {
+    if (piece + 1 < p_end) {
       stage(piece + 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
@@ -477,8 +505,8 @@ perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uin
     const uint16_t* jb = jbuf[piece & 1] + lane;
     const uint32_t* cb = cbuf[piece & 1];
     const int c0 = piece * (kStageSteps / 32);
-    const int cend = min(kStageSteps / 32, nchunks - c0);
-    const int nfull = min(cend, (nsteps - c0 * 32) >> 5);  // chunks of this piece with all 32 steps
+    const int cend = min(kStageSteps / 32, nch_end - c0);
+    const int nfull = min(cend, (ke - c0 * 32) >> 5);  // chunks of this piece with all 32 steps
     uint16_t* slotp = perm + ((L - 1) - (c0 * 32 + lane));  // this lane's own slot; moves down 32 slots per chunk
     int jn = jb[0];
     uint32_t cn = cb[0];
@@ -518,10 +546,10 @@ perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uin
       }
       slotp -= 32;
     }
-    if (nfull < cend) {  // the utterance's last, partial chunk
+    if (nfull < cend) {  // the utterance's last, partial chunk (only the last phase can end inside a chunk)
       const int j = jn;
       uint32_t cut = cn;
-      const int nvalid = nsteps - (c0 + nfull) * 32;
+      const int nvalid = ke - (c0 + nfull) * 32;
       int s0 = 0;
       for (;;) {
         const int s1 = cut ? min(__ffs(cut) - 1, nvalid) : nvalid;
@@ -544,7 +572,12 @@ perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uin
     __syncwarp();  // everyone is done with this stage buffer before it is refilled two pieces later
   }
   __syncwarp();
-  for (int k = lane; k < n; k += 32) isd_idx[beg + k] = (int32_t)perm[k];
+  if (!last) {  // hand the array on (whole pieces of 8 entries; the rows are padded)
+    for (int k = 8 * lane; k < live; k += 256) *reinterpret_cast<uint4*>(state + k) = *reinterpret_cast<const uint4*>(perm + k);
+    return;
+  }
+  // the first n slots: what this phase holds comes from shared memory, slots finalised earlier from the state array
+  for (int k = lane; k < n; k += 32) isd_idx[beg + k] = (int32_t)(k < live ? perm[k] : __ldcg(state + k));
 }
 
 // ---- genNotchCoeffs arithmetic (RawBoost.py:37-47), one CTA per filter, float64 -------------------------------------------
@@ -656,7 +689,7 @@ design_kernel(int nBands, double fs, int n_filters, const double* __restrict__ p
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct DevPlanLayout {
-  size_t lnl_params, lnl_cnt, lnl_off, lnl_taps, isd_cnt, isd_off, isd_idx, isd_fr, isd_jseq, isd_cuts, ssi_noise, ssi_params,
+  size_t lnl_params, lnl_cnt, lnl_off, lnl_taps, isd_cnt, isd_off, isd_idx, isd_fr, isd_jseq, isd_cuts, isd_state, ssi_noise, ssi_params,
       ssi_cnt, ssi_off, ssi_taps, ssi_snr, bytes;
   int jld, cuts_ld;
 };
@@ -689,6 +722,7 @@ DevPlanLayout layout(const rb_args& a, int algo, int B, int ld) {
   l.cuts_ld = l.jld / 32;
   l.isd_jseq = take(isd ? (size_t)B * l.jld * 2 : 0);
   l.isd_cuts = take(isd ? (size_t)B * l.cuts_ld * 4 : 0);
+  l.isd_state = take(isd ? (size_t)B * l.jld * 2 : 0);
   l.ssi_noise = take(ssi ? (size_t)B * ld * 4 : 0);
   l.ssi_params = take(ssi ? (size_t)B * stride * 8 : 0);
   l.ssi_cnt = take(ssi ? (size_t)B * 4 : 0);
@@ -809,13 +843,21 @@ int devplan_apply(const rb_args* args, int algo, int B, int ld, const int32_t* l
   if (!isd || count <= 0) return RB_OK;
   const DevPlanLayout l = layout(*args, algo, B, ld);
   char* d = (char*)storage;
-  const size_t smem = 2 * kStageSteps * 2 + 2 * (kStageSteps / 32) * 4 + align_up((size_t)ld * 2 + 4, 16);
-  if (smem > 227 * 1024) return RB_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024) RB_CUDA(cudaFuncSetAttribute(perm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  perm_apply_kernel<<<count, 32, smem, st>>>(count, l.jld, len + first, (const uint16_t*)(d + l.isd_jseq) + (size_t)first * l.jld,
-                                            (const uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld,
-                                            (const int32_t*)(d + l.isd_off) + first, (int32_t*)(d + l.isd_idx));
-  RB_LAUNCH_CHECK();
+  static const int kPhaseT[5] = {65536, 49152, 32768, 16384, 0};
+  RB_CUDA(cudaFuncSetAttribute(perm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  RB_CUDA(cudaFuncSetAttribute(perm_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  for (int ph = 0; ph < 4; ++ph) {
+    const int T_hi = kPhaseT[ph], T_lo = kPhaseT[ph + 1];
+    if (T_lo >= ld) continue;  // no utterance of this batch has slots that high
+    const size_t entries = (size_t)std::min(T_hi, (ld + 7) / 8 * 8) + 8;  // + the uint4 tail of the state copy
+    const size_t smem = 2 * kStageSteps * 2 + 2 * (kStageSteps / 32) * 4 + 64 + align_up(entries * 2, 16);
+    if (smem > 227 * 1024) return RB_ERR_UNSUPPORTED;
+    perm_apply_kernel<<<count, 32, smem, st>>>(count, l.jld, len + first, (const uint16_t*)(d + l.isd_jseq) + (size_t)first * l.jld,
+                                              (const uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld,
+                                              (const int32_t*)(d + l.isd_off) + first, (int32_t*)(d + l.isd_idx),
+                                              (uint16_t*)(d + l.isd_state) + (size_t)first * l.jld, T_hi, T_lo);
+    RB_LAUNCH_CHECK();
+  }
   return RB_OK;
 }
 
