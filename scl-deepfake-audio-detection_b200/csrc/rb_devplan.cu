@@ -448,6 +448,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 // 64 and 32 KB -- so that 1, 2, 3 and 6 utterances per SM are in flight instead of one throughout (the kernel is bound by
 // the latency of a single warp per utterance). The array travels between phases through `state` (global, L2-resident);
 // every phase writes back all it holds, so slots finalised in an earlier phase keep their final value there.
+constexpr int kJStride = kStageSteps + 32;       // uint16 entries per target staging buffer
+constexpr int kCStride = kStageSteps / 32 + 4;   // uint32 entries per group-mask staging buffer
+constexpr int kApplyStageBytes = 2 * kJStride * 2 + 2 * kCStride * 4;
+static_assert((kJStride * 2) % 16 == 0 && (kCStride * 4) % 16 == 0 && kApplyStageBytes % 16 == 0, "cp.async alignment");
+
 __device__ __forceinline__ int phase_first_step(int L, int T) {  // first step (multiple of 1024) whose slot is below T
   const int k = L - T;
   return k <= 0 ? 0 : (k + kStageSteps - 1) / kStageSteps * kStageSteps;
@@ -458,9 +463,10 @@ perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uin
                   const uint32_t* __restrict__ cuts_all, int cuts_ld, const int32_t* __restrict__ isd_off,
                   int32_t* __restrict__ isd_idx, uint16_t* __restrict__ state_all, int T_hi, int T_lo) {
   extern __shared__ __align__(16) unsigned char dyn[];
-  uint16_t (*jbuf)[kStageSteps] = reinterpret_cast<uint16_t (*)[kStageSteps]>(dyn);                       // [2][1024]
-  uint32_t (*cbuf)[kStageSteps / 32] = reinterpret_cast<uint32_t (*)[kStageSteps / 32]>(dyn + 2 * kStageSteps * 2);  // [2][32]
-  uint16_t* perm = reinterpret_cast<uint16_t*>(dyn + 2 * kStageSteps * 2 + 2 * (kStageSteps / 32) * 4 + 64);  // 64 B: read-ahead slack
+  // two staging buffers for targets and group masks, each with one chunk of padding for the one-ahead reads of the loop below
+  uint16_t (*jbuf)[kJStride] = reinterpret_cast<uint16_t (*)[kJStride]>(dyn);
+  uint32_t (*cbuf)[kCStride] = reinterpret_cast<uint32_t (*)[kCStride]>(dyn + 2 * kJStride * 2);
+  uint16_t* perm = reinterpret_cast<uint16_t*>(dyn + kApplyStageBytes);
   const int u = blockIdx.x, lane = threadIdx.x;
   const int L = len_arr[u];
   const int beg = isd_off[u], n = isd_off[u + 1] - beg;
@@ -510,14 +516,13 @@ perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uin
     uint16_t* slotp = perm + ((L - 1) - (c0 * 32 + lane));  // this lane's own slot; moves down 32 slots per chunk
     int jn = jb[0];
     uint32_t cn = cb[0];
-    // Full chunks. The next chunk's target and group mask are fetched one iteration ahead (reads past the piece's last
-    // chunk stay inside the staging buffers and are never used); the common case -- no conflict inside the chunk, 93 % of
-    // them -- is two loads and two stores per lane.
+    // Full chunks. The next chunk's target and group mask are fetched one iteration ahead; the common case -- no conflict
+    // inside the chunk, 93 % of them -- is two loads and two stores per lane.
 #pragma unroll 4
     for (int cc = 0; cc < nfull; ++cc) {
       const int j = jn;
       uint32_t cut = cn;
-      jn = jb[(cc + 1) * 32];
+      jn = jb[(cc + 1) * 32];  // past the piece's last chunk this reads the buffer's own padding (never used)
       cn = cb[cc + 1];
       if (cut == 0u) {
         const uint16_t va = perm[j], vb = *slotp;
@@ -850,7 +855,7 @@ int devplan_apply(const rb_args* args, int algo, int B, int ld, const int32_t* l
     const int T_hi = kPhaseT[ph], T_lo = kPhaseT[ph + 1];
     if (T_lo >= ld) continue;  // no utterance of this batch has slots that high
     const size_t entries = (size_t)std::min(T_hi, (ld + 7) / 8 * 8) + 8;  // + the uint4 tail of the state copy
-    const size_t smem = 2 * kStageSteps * 2 + 2 * (kStageSteps / 32) * 4 + 64 + align_up(entries * 2, 16);
+    const size_t smem = kApplyStageBytes + align_up(entries * 2, 16);
     if (smem > 227 * 1024) return RB_ERR_UNSUPPORTED;
     perm_apply_kernel<<<count, 32, smem, st>>>(count, l.jld, len + first, (const uint16_t*)(d + l.isd_jseq) + (size_t)first * l.jld,
                                               (const uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld,
