@@ -18,7 +18,6 @@
 #include <math.h>
 #include <string.h>
 #include <atomic>
-#include <complex>
 #include <thread>
 #include <vector>
 
@@ -130,56 +129,57 @@ struct Mt {
 };
 
 // ---- filter design ------------------------------------------------------------------------------------------------
-void fft1024(std::complex<double>* a) {  // in-place radix-2 DIT, n = 1024
-  constexpr int n = 1024;
-  static std::complex<double> tw[n / 2];
-  static std::atomic<int> ready{0};
-  static std::atomic<int> lock{0};
-  if (!ready.load(std::memory_order_acquire)) {
-    int expected = 0;
-    if (lock.compare_exchange_strong(expected, 1)) {
-      for (int k = 0; k < n / 2; ++k) tw[k] = std::complex<double>(cos(-2.0 * M_PI * k / n), sin(-2.0 * M_PI * k / n));
-      ready.store(1, std::memory_order_release);
-    } else {
-      while (!ready.load(std::memory_order_acquire)) {
-      }
+// |H| peak on scipy.signal.freqz's default grid (512 points on [0, pi)): the first half of a 1024-point DFT of the taps.
+// Radix-2 decimation in time on split real / imaginary arrays (plain double arithmetic: std::complex products without
+// -ffast-math go through __muldc3 and cost several times more). Direct evaluation for cascades longer than 1024 taps.
+struct Twiddles {
+  double c[512], s[512];
+  Twiddles() {
+    for (int k = 0; k < 512; ++k) {
+      c[k] = cos(-2.0 * M_PI * k / 1024.0);
+      s[k] = sin(-2.0 * M_PI * k / 1024.0);
     }
   }
-  for (int i = 1, j = 0; i < n; ++i) {
-    int bit = n >> 1;
-    for (; j & bit; bit >>= 1) j ^= bit;
-    j ^= bit;
-    if (i < j) std::swap(a[i], a[j]);
-  }
-  for (int len = 2; len <= n; len <<= 1) {
-    const int step = n / len;
-    for (int i = 0; i < n; i += len)
-      for (int k = 0; k < len / 2; ++k) {
-        const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * tw[k * step];
-        a[i + k] = u + v;
-        a[i + k + len / 2] = u - v;
-      }
-  }
-}
+};
 
-// max |H(w)| on scipy.signal.freqz's default grid (512 points on [0, pi)); FFT path for K <= 1024, direct otherwise.
 double peak_response(const std::vector<double>& b) {
   const int K = (int)b.size();
   double best = 0.0;
   if (K <= 1024) {
-    std::complex<double> buf[1024];
-    for (int i = 0; i < 1024; ++i) buf[i] = std::complex<double>(i < K ? b[i] : 0.0, 0.0);
-    fft1024(buf);
-    for (int i = 0; i < 512; ++i) best = fmax(best, std::abs(buf[i]));
+    static const Twiddles tw;  // thread-safe one-time initialisation
+    constexpr int n = 1024;
+    double re[n], im[n];
+    for (int i = 0, j = 0; i < n; ++i) {  // bit-reversed load of the real input
+      re[j] = i < K ? b[i] : 0.0;
+      im[j] = 0.0;
+      int bit = n >> 1;
+      for (; j & bit; bit >>= 1) j ^= bit;
+      j ^= bit;
+    }
+    for (int len = 2; len <= n; len <<= 1) {
+      const int half = len >> 1, step = n / len;
+      for (int i = 0; i < n; i += len)
+        for (int k = 0; k < half; ++k) {
+          const double wr = tw.c[k * step], wi = tw.s[k * step];
+          const double xr = re[i + k + half], xi = im[i + k + half];
+          const double tr = xr * wr - xi * wi, ti = xr * wi + xi * wr;
+          const double ur = re[i + k], ui = im[i + k];
+          re[i + k] = ur + tr;
+          im[i + k] = ui + ti;
+          re[i + k + half] = ur - tr;
+          im[i + k + half] = ui - ti;
+        }
+    }
+    for (int i = 0; i < 512; ++i) best = fmax(best, hypot(re[i], im[i]));
   } else {
     for (int i = 0; i < 512; ++i) {
       const double w = M_PI * i / 512.0;
-      double re = 0.0, im = 0.0;
+      double sr = 0.0, si = 0.0;
       for (int k = 0; k < K; ++k) {
-        re += b[k] * cos(w * k);
-        im -= b[k] * sin(w * k);
+        sr += b[k] * cos(w * k);
+        si -= b[k] * sin(w * k);
       }
-      best = fmax(best, hypot(re, im));
+      best = fmax(best, hypot(sr, si));
     }
   }
   return best;
