@@ -212,21 +212,41 @@ isd_scatter_kernel(const float* __restrict__ raw, const int32_t* __restrict__ le
 // utterance) are read a second time, last-read first, while they are still in L2 (2 CTAs/SM x 148 SMs x 126 KB = 37 MB of
 // re-read footprint). HBM traffic is therefore close to the algorithmic read-once / write-once; two CTAs per SM overlap one
 // utterance's load phase with the other's store phase. The impulse bit mask lives in shared memory.
-constexpr int kFusedThreads = 512;
-constexpr int kParkSmem = 9;   // chunks per thread parked in shared memory
-constexpr int kParkRegs = 4;   // chunks per thread kept in registers
+// (the RB_ISD_* macros exist for variant experiments: scripts/gpu_variants.sh style builds with RB_EXTRA_FLAGS)
+#ifndef RB_ISD_THREADS
+#define RB_ISD_THREADS 512
+#endif
+#ifndef RB_ISD_PARK_SMEM
+#define RB_ISD_PARK_SMEM 9
+#endif
+#ifndef RB_ISD_PARK_REGS
+#define RB_ISD_PARK_REGS 4
+#endif
+#ifndef RB_ISD_OVER_U
+#define RB_ISD_OVER_U 6
+#endif
+#ifndef RB_ISD_MIN_BLOCKS
+#define RB_ISD_MIN_BLOCKS 2
+#endif
+constexpr int kFusedThreads = RB_ISD_THREADS;
+constexpr int kParkSmem = RB_ISD_PARK_SMEM;   // chunks per thread parked in shared memory
+constexpr int kParkRegs = RB_ISD_PARK_REGS;   // chunks per thread kept in registers
 constexpr int kParkChunks = (kParkSmem + kParkRegs) * kFusedThreads;  // float4 chunks resident on chip (32768 samples)
-constexpr int kOverU = 6;      // overflow chunks in flight per thread
+constexpr int kOverU = RB_ISD_OVER_U;         // overflow chunks in flight per thread
+#ifndef RB_ISD_IMP_U
+#define RB_ISD_IMP_U 4
+#endif
+constexpr int kImpU = RB_ISD_IMP_U;           // impulses in flight per thread in the mask / gather / scatter loops
 constexpr int kStash = 6528;   // impulse values kept in shared memory between the peak and the scatter (P = 10 % of 64600 = 6460)
 
-__global__ void __launch_bounds__(kFusedThreads, 2)
+__global__ void __launch_bounds__(kFusedThreads, RB_ISD_MIN_BLOCKS)
 isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, int always,
                  const int32_t* __restrict__ isd_off, const int32_t* __restrict__ isd_idx, const double* __restrict__ isd_fr,
                  float g_sd, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char dynsm[];
   float4* park = reinterpret_cast<float4*>(dynsm);                                                  // [kParkSmem][512]
-  float* stash = reinterpret_cast<float*>(dynsm + (size_t)kParkSmem * kFusedThreads * 16);          // [kStash]
-  uint32_t* smask = reinterpret_cast<uint32_t*>(stash + kStash);                                    // [ceil(len/32)]
+  float* stash = reinterpret_cast<float*>(dynsm + (size_t)kParkSmem * kFusedThreads * 16);          // [kStash]     } only with
+  uint32_t* smask = reinterpret_cast<uint32_t*>(stash + kStash);                                    // [ceil(len/32)] } impulses
   __shared__ float red[kFusedThreads / 32][2];
   __shared__ float bc[3];
   const int u = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -255,7 +275,7 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
   // Everything that fits on chip is requested at once: the parked chunks go global -> shared by cp.async (no registers
   // involved, so all nine per thread are in flight together), the kept chunks into registers. The impulse mask is built
   // while they travel.
-  float4 keep[kParkRegs];
+  float4 keep[kParkRegs > 0 ? kParkRegs : 1];
   {
 #pragma unroll
     for (int k = 0; k < kParkSmem; ++k) {
@@ -275,9 +295,16 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
       const int nwords = (len + 31) >> 5;
       for (int w = tid; w < nwords; w += kFusedThreads) smask[w] = 0u;
       __syncthreads();
-      for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
-        const int p = isd_idx[i];
-        if (p >= 0 && p < len) atomicOr(smask + (p >> 5), 1u << (p & 31));
+      for (int i0 = ibeg + tid; i0 < iend; i0 += kImpU * kFusedThreads) {  // kImpU positions in flight per thread
+        int p[kImpU];
+#pragma unroll
+        for (int k = 0; k < kImpU; ++k) {
+          const int i = i0 + k * kFusedThreads;
+          p[k] = (i < iend) ? __ldg(isd_idx + i) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < kImpU; ++k)
+          if (p[k] >= 0 && p[k] < len) atomicOr(smask + (p[k] >> 5), 1u << (p[k] & 31));
       }
     }
     if (with_isd) __syncthreads();  // mask complete
@@ -344,13 +371,29 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
     __syncthreads();  // the parked chunks of other threads
     const float* parked = reinterpret_cast<const float*>(park);
     float mt = 0.f;
-    for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
-      const int p = isd_idx[i];
-      if (p >= 0 && p < len) {
-        const float xv = (p < kParkSmem * kFusedThreads * 4) ? parked[p] : __ldg(row + p);
-        const float t = isd_value(__fdiv_rn(xv, div1), g_sd, isd_fr[i]);
-        mt = fmaxf(mt, fabsf(t));
-        if (i - ibeg < kStash) stash[i - ibeg] = t;
+    for (int i0 = ibeg + tid; i0 < iend; i0 += kImpU * kFusedThreads) {  // loads of kImpU impulses issued before their use
+      int p[kImpU];
+      double fr[kImpU];
+      float xv[kImpU];
+#pragma unroll
+      for (int k = 0; k < kImpU; ++k) {
+        const int i = i0 + k * kFusedThreads;
+        p[k] = (i < iend) ? __ldg(isd_idx + i) : -1;
+        if (p[k] >= len) p[k] = -1;
+      }
+#pragma unroll
+      for (int k = 0; k < kImpU; ++k) {
+        fr[k] = (p[k] >= 0) ? __ldg(isd_fr + i0 + k * kFusedThreads) : 0.0;
+        xv[k] = (p[k] < 0) ? 0.f : (p[k] < kParkSmem * kFusedThreads * 4) ? parked[p[k]] : __ldg(row + p[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < kImpU; ++k) {
+        if (p[k] >= 0) {
+          const int i = i0 + k * kFusedThreads;
+          const float t = isd_value(__fdiv_rn(xv[k], div1), g_sd, fr[k]);
+          mt = fmaxf(mt, fabsf(t));
+          if (i - ibeg < kStash) stash[i - ibeg] = t;
+        }
       }
     }
     mt = warp_max(mt);
@@ -402,11 +445,20 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
   for (int k = 0; k < kParkSmem; ++k) store_chunk(park[k * kFusedThreads + tid], k * kFusedThreads + tid);
   if (with_isd) {
     __syncthreads();  // impulse positions overwrite what the dense pass just stored (merged in L2 before reaching HBM)
-    for (int i = ibeg + tid; i < iend; i += kFusedThreads) {
-      const int p = isd_idx[i];
-      if (p >= 0 && p < len) {
-        const float t = (i - ibeg < kStash) ? stash[i - ibeg] : isd_value(__fdiv_rn(__ldg(row + p), div1), g_sd, isd_fr[i]);
-        orow[p] = __fdiv_rn(t, div2);
+    for (int i0 = ibeg + tid; i0 < iend; i0 += kImpU * kFusedThreads) {
+      int p[kImpU];
+#pragma unroll
+      for (int k = 0; k < kImpU; ++k) {
+        const int i = i0 + k * kFusedThreads;
+        p[k] = (i < iend) ? __ldg(isd_idx + i) : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < kImpU; ++k) {
+        const int i = i0 + k * kFusedThreads;
+        if (p[k] >= 0 && p[k] < len) {
+          const float t = (i - ibeg < kStash) ? stash[i - ibeg] : isd_value(__fdiv_rn(__ldg(row + p[k]), div1), g_sd, isd_fr[i]);
+          orow[p[k]] = __fdiv_rn(t, div2);
+        }
       }
     }
   }
@@ -499,8 +551,8 @@ namespace rb {
 int launch_isd_fused(const float* x, const int32_t* len, int B, int ld, int always, const int32_t* isd_off, const int32_t* isd_idx,
                      const double* isd_fr, float g_sd, float* out, cudaStream_t st) {
   if (B <= 0) return RB_OK;
-  const size_t smem = (size_t)kParkSmem * kFusedThreads * 16 + kStash * 4 + (isd_off ? ((size_t)(ld + 31) / 32) * 4 : 0);
-  if (smem > 113 * 1024) return RB_ERR_UNSUPPORTED;  // keeps two CTAs per SM; longer rows take the multi-pass path
+  const size_t smem = (size_t)kParkSmem * kFusedThreads * 16 + (isd_off ? kStash * 4 + ((size_t)(ld + 31) / 32) * 4 : 0);
+  if (smem > (227 / RB_ISD_MIN_BLOCKS) * 1024) return RB_ERR_UNSUPPORTED;  // keeps two CTAs per SM; longer rows take the multi-pass path
   RB_CUDA(cudaFuncSetAttribute(isd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // without this the driver may pick a carve-out that holds a single CTA per SM
   RB_CUDA(cudaFuncSetAttribute(isd_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
