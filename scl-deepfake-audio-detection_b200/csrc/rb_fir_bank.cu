@@ -60,6 +60,30 @@ __device__ __forceinline__ float pow_round_once(float v, int p) {
 #endif
 }
 
+// xp[j] = x1[j] ** kPow over the whole staged range, four samples per step (LDS.128 / STS.128, the multiply chain unrolled).
+// Same arithmetic as pow_round_once: fp64 products in the same order, rounded to fp32 once.
+template <int kPow>
+__device__ __forceinline__ void stage_power(float* __restrict__ xp, const float* __restrict__ x1) {
+  static_assert(kXS % 4 == 0, "staged range must be whole float4 chunks");
+#ifdef RB_POW_FP32
+  for (int j = threadIdx.x; j < kXS; j += kThreads) xp[j] = pow_round_once(x1[j], kPow);
+#else
+  for (int c = threadIdx.x; c < kXS / 4; c += kThreads) {
+    const float4 v = reinterpret_cast<const float4*>(x1)[c];
+    const double d0 = (double)v.x, d1 = (double)v.y, d2 = (double)v.z, d3 = (double)v.w;
+    double a0 = d0, a1 = d1, a2 = d2, a3 = d3;
+#pragma unroll
+    for (int i = 1; i < kPow; ++i) {
+      a0 *= d0;
+      a1 *= d1;
+      a2 *= d2;
+      a3 *= d3;
+    }
+    reinterpret_cast<float4*>(xp)[c] = make_float4((float)a0, (float)a1, (float)a2, (float)a3);
+  }
+#endif
+}
+
 // Stage x[gbase .. gbase+kXS) of one utterance row into smem, zero outside [0, len).
 __device__ __forceinline__ void stage_x(float* __restrict__ dst, const float* __restrict__ row, int len, int gbase) {
   // gbase is a multiple of 4 and the row is 16-byte aligned, so every chunk is an aligned float4.
@@ -256,7 +280,14 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       const float* src = sm.x1;
       if (power != 1) {
         if (staged_pow != power) {
-          for (int j = tid; j < kXS; j += kThreads) sm.xp[j] = pow_round_once(sm.x1[j], power);
+          switch (power) {  // uniform; the LnL bank uses 2..N_f
+            case 2: stage_power<2>(sm.xp, sm.x1); break;
+            case 3: stage_power<3>(sm.xp, sm.x1); break;
+            case 4: stage_power<4>(sm.xp, sm.x1); break;
+            case 5: stage_power<5>(sm.xp, sm.x1); break;
+            default:
+              for (int j = tid; j < kXS; j += kThreads) sm.xp[j] = pow_round_once(sm.x1[j], power);
+          }
           staged_pow = power;
         }
         src = sm.xp;
