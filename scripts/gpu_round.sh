@@ -1,5 +1,5 @@
 # full GPU check: tests, smoke, default bench, per-algo values, ncu evidence
-tag=${1:-r01v7}
+tag=${1:-r02v1}
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
