@@ -170,7 +170,23 @@ double peak_response(const std::vector<double>& b) {
           im[i + k + half] = ui - ti;
         }
     }
-    for (int i = 0; i < 512; ++i) best = fmax(best, hypot(re[i], im[i]));
+    // max |H|: hypot is the expensive part, so squared magnitudes pick the candidates first. A bin whose squared magnitude is
+    // more than 1e-12 (relative) below the largest cannot hold the maximum of hypot (whose error is ~1e-16), so the result
+    // is the same value the full scan returns.
+    double m2[512], m2max = 0.0;
+    bool finite = true;
+    for (int i = 0; i < 512; ++i) {
+      m2[i] = re[i] * re[i] + im[i] * im[i];
+      finite &= (m2[i] <= 1.0e300);  // false for inf / NaN too
+      m2max = fmax(m2max, m2[i]);
+    }
+    if (finite && m2max >= 1.0e-280) {
+      const double cut = m2max * (1.0 - 1.0e-12);
+      for (int i = 0; i < 512; ++i)
+        if (m2[i] >= cut) best = fmax(best, hypot(re[i], im[i]));
+    } else {  // squares over- or underflow: plain scan
+      for (int i = 0; i < 512; ++i) best = fmax(best, hypot(re[i], im[i]));
+    }
   } else {
     for (int i = 0; i < 512; ++i) {
       const double w = M_PI * i / 512.0;
@@ -191,21 +207,61 @@ inline double sinc_pi(double x) {  // numpy.sinc
   return sin(y) / y;
 }
 
+// Values that depend on the stage length only, computed once per length and thread: the Hamming window
+// 0.54 - 0.46 cos(2 pi i / (n - 1)) and, for odd n, numpy.sinc at the integer offsets m = i - (n - 1) / 2.
+struct FirwinCache {
+  static constexpr int kMaxN = 256;
+  std::vector<double> win[kMaxN + 1];
+  double sinc_int[kMaxN + 1];  // sinc_pi(m), m = 0 .. kMaxN
+  FirwinCache() {
+    for (int m = 0; m <= kMaxN; ++m) sinc_int[m] = sinc_pi(1.0 * m);
+  }
+  const std::vector<double>& window(int n) {
+    std::vector<double>& w = win[n];
+    if (w.empty()) {
+      w.resize(n);
+      for (int i = 0; i < n; ++i) w[i] = (n == 1) ? 1.0 : 0.54 - 0.46 * cos(2.0 * M_PI * i / (n - 1));
+    }
+    return w;
+  }
+};
+
 // scipy.signal.firwin(n, [f1, f2], window='hamming', fs=fs) with the default pass_zero=True: a band-stop, DC gain 1.
+// Every value is produced by the same operations in the same order as the plain loop over i; the sinc terms are even in
+// m (glibc's sin is odd, the products and the quotient only change sign), so for odd n the upper half is copied from the lower.
 void firwin_bandstop(int n, double f1, double f2, double fs, std::vector<double>& h) {
   const double nyq = fs / 2.0, c1 = f1 / nyq, c2 = f2 / nyq, alpha = 0.5 * (n - 1);
   h.resize(n);
   double dc = 0.0;
-  for (int i = 0; i < n; ++i) {
-    const double m = i - alpha;
-    // bands [0, c1] and [c2, 1]
-    double v = c1 * sinc_pi(c1 * m);  // same association as scipy's loop over the bands
-    v -= 0.0 * sinc_pi(0.0 * m);
-    v += 1.0 * sinc_pi(1.0 * m);
-    v -= c2 * sinc_pi(c2 * m);
-    const double win = (n == 1) ? 1.0 : 0.54 - 0.46 * cos(2.0 * M_PI * i / (n - 1));
-    h[i] = v * win;
-    dc += h[i];  // scale_frequency = 0 -> cos term is 1
+  if ((n & 1) && n <= FirwinCache::kMaxN) {
+    thread_local FirwinCache cache;
+    const std::vector<double>& win = cache.window(n);
+    const int half = (n - 1) / 2;  // = alpha
+    for (int i = 0; i <= half; ++i) {
+      const double m = i - alpha;  // integer, <= 0
+      double v = c1 * sinc_pi(c1 * m);
+      v -= 0.0 * 1.0;              // 0.0 * sinc_pi(0.0 * m): sinc_pi(+-0) = 1
+      v += 1.0 * cache.sinc_int[half - i];
+      v -= c2 * sinc_pi(c2 * m);
+      h[i] = v;
+      h[n - 1 - i] = v;
+    }
+    for (int i = 0; i < n; ++i) {
+      h[i] = h[i] * win[i];
+      dc += h[i];  // scale_frequency = 0 -> cos term is 1
+    }
+  } else {
+    for (int i = 0; i < n; ++i) {
+      const double m = i - alpha;
+      // bands [0, c1] and [c2, 1]
+      double v = c1 * sinc_pi(c1 * m);  // same association as scipy's loop over the bands
+      v -= 0.0 * sinc_pi(0.0 * m);
+      v += 1.0 * sinc_pi(1.0 * m);
+      v -= c2 * sinc_pi(c2 * m);
+      const double win = (n == 1) ? 1.0 : 0.54 - 0.46 * cos(2.0 * M_PI * i / (n - 1));
+      h[i] = v * win;
+      dc += h[i];  // scale_frequency = 0 -> cos term is 1
+    }
   }
   for (int i = 0; i < n; ++i) h[i] /= dc;
 }
