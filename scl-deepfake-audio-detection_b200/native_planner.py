@@ -20,11 +20,14 @@ from .plans import ALGO_USES_ISD, ALGO_USES_LNL, ALGO_USES_SSI, BatchPlan, padde
 _args_struct = _lib.args_struct
 
 
+_MT_STATE_BYTES = 624 * 4 + 4  # numpy's mt19937_state: uint32 key[624]; int pos (numpy/random/src/mt19937/mt19937.h)
+
+
 def _view(ptr, n, dtype):
     if not ptr or n == 0:
         return np.zeros(0, dtype=dtype)
-    ct = {np.float32: C.c_float, np.int32: C.c_int32, np.float64: C.c_double}[dtype]
-    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,))
+    addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+    return np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr), dtype=dtype)  # a view, no copy
 
 
 class NativePlanner:
@@ -52,17 +55,34 @@ class NativePlanner:
             if seeds_arr.shape[0] != B:
                 raise ValueError("one seed per utterance")
         elif use_global_stream:
-            name, key, pos, has_gauss, cached = np.random.get_state()
             state = _lib.RbRngState()
-            C.memmove(state.key, np.ascontiguousarray(key, dtype=np.uint32).ctypes.data, 624 * 4)
-            state.pos, state.has_gauss, state.cached_gaussian = int(pos), int(has_gauss), float(cached)
+            bitgen = np.random.mtrand._rand._bit_generator
+            # Without SSI no normal is drawn, so the legacy Gaussian cache is neither read nor written and the 624 words + cursor
+            # can be exchanged directly with the bit generator's own mt19937_state {uint32 key[624]; int pos;} under its
+            # lock (np.random.get_state() / set_state() cost ~70 us each, more than the LnL draw itself).
+            direct = algo not in ALGO_USES_SSI and type(bitgen).__name__ == "MT19937"
+            if direct:
+                bitgen.lock.acquire()
+                state_addr = bitgen.ctypes.state_address
+                C.memmove(C.byref(state), state_addr, _MT_STATE_BYTES)
+                state.has_gauss, state.cached_gaussian = 0, 0.0
+            else:
+                name, key, pos, has_gauss, cached = np.random.get_state()
+                C.memmove(state.key, np.ascontiguousarray(key, dtype=np.uint32).ctypes.data, 624 * 4)
+                state.pos, state.has_gauss, state.cached_gaussian = int(pos), int(has_gauss), float(cached)
         else:
             raise ValueError("give per-utterance seeds or use_global_stream=True")
-        rc = self.lib.rb_planner_draw(self._h, C.byref(a), int(algo), B, ld, C.c_void_p(lengths.ctypes.data),
-                                      C.c_void_p(seeds_arr.ctypes.data) if seeds_arr is not None else None,
-                                      C.byref(state) if state is not None else None, C.byref(view))
-        _lib.check(rc, "rb_planner_draw")
-        if state is not None:
+        try:
+            rc = self.lib.rb_planner_draw(self._h, C.byref(a), int(algo), B, ld, C.c_void_p(lengths.ctypes.data),
+                                          C.c_void_p(seeds_arr.ctypes.data) if seeds_arr is not None else None,
+                                          C.byref(state) if state is not None else None, C.byref(view))
+            _lib.check(rc, "rb_planner_draw")
+            if state is not None and direct:
+                C.memmove(state_addr, C.byref(state), _MT_STATE_BYTES)
+        finally:
+            if state is not None and direct:
+                bitgen.lock.release()
+        if state is not None and not direct:
             key = np.frombuffer(bytes(state.key), dtype=np.uint32).copy()
             np.random.set_state(("MT19937", key, int(state.pos), int(state.has_gauss), float(state.cached_gaussian)))
         bp = BatchPlan(B=B, ld=ld, lengths=lengths, g_sd=float(args.g_sd) if algo in ALGO_USES_ISD else 0.0)
