@@ -263,6 +263,19 @@ def test_native_planner_continues_the_global_numpy_stream(P, native, golden):
     got = np.random.get_state()
     _same_plan(a, b)
     assert np.array_equal(ref_state[1], got[1]) and ref_state[2:] == got[2:]
+    # algos without SSI exchange the words directly with numpy's bit generator: a pending cached gaussian must survive untouched
+    for algo in (1, 2, 5, 8):
+        tails = []
+        for draw in (lambda: P.draw_batch([777, 64600], 16000, ARGS, algo),
+                     lambda: native.draw([777, 64600], 16000, ARGS, algo, use_global_stream=True, copy=True)):
+            np.random.seed(11)
+            np.random.normal()                      # leaves the second value of the pair cached
+            plan = draw()
+            st = np.random.get_state()
+            assert st[3] == 1                        # still cached
+            tails.append((plan, st[1].copy(), st[2:], np.random.normal(), np.random.uniform()))
+        _same_plan(tails[1][0], tails[0][0])
+        assert np.array_equal(tails[0][1], tails[1][1]) and tails[0][2:] == tails[1][2:]
 
 
 def test_native_planner_nondefault_args(P, native):
