@@ -35,25 +35,34 @@ def functions(path):
         yield name, cur
 
 
+def body_loop(ins):
+    """The FFMA2 body loop of a kernel: the backward-branch loop whose instructions are mostly FFMA2 (None if there is none)."""
+    loops = []
+    for a, t, _ in ins:
+        m = re.search(r"BRA\S*\s+(?:\S+,\s+)?0x([0-9a-f]+)", t)
+        if m and int(m.group(1), 16) < a:
+            loops.append((int(m.group(1), 16), a))
+    if not loops:
+        return None
+
+    def density(loop):
+        b = [x for x in ins if loop[0] <= x[0] <= loop[1]]
+        f = sum("FFMA2" in t for _, t, _ in b)
+        return (f / len(b) if f >= 100 else 0.0, f)
+
+    lo, hi_addr = max(loops, key=density)
+    return [x for x in ins if lo <= x[0] <= hi_addr]
+
+
 def main():
     path = sys.argv[1] if len(sys.argv) > 1 else LIB
     for name, ins in functions(path):
         if "fir_bank_kernel" not in name:
             continue
-        loops = []
-        for a, t, _ in ins:
-            m = re.search(r"BRA\S*\s+(?:\S+,\s+)?0x([0-9a-f]+)", t)
-            if m and int(m.group(1), 16) < a:
-                loops.append((a - int(m.group(1), 16), int(m.group(1), 16), a))
-        if not loops:
+        body = body_loop(ins)
+        if not body:
             continue
-        # the body loop: the backward-branch loop whose instructions are mostly FFMA2
-        def density(loop):
-            b = [x for x in ins if loop[1] <= x[0] <= loop[2]]
-            f = sum("FFMA2" in t for _, t, _ in b)
-            return (f / len(b) if f >= 100 else 0.0, f)
-        _, lo, hi_addr = max(loops, key=density)
-        body = [x for x in ins if lo <= x[0] <= hi_addr]
+        lo, hi_addr = body[0][0], body[-1][0]
         mix = collections.Counter((t.split()[1] if t.startswith("@") else t.split()[0]) for _, t, _ in body)
         ff = [x for x in body if "FFMA2" in x[1]]
         reuse = sum("reuse" in t for _, t, _ in ff)

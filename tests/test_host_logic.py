@@ -350,3 +350,32 @@ def test_header_is_plain_c(tmp_path):
     out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+# -----------------------------------------------------------------------------------------------------------------------------
+# the compiled FIR-bank kernel keeps its shape: packed FFMA2 body loop, no spills, 4 CTAs per SM worth of registers
+def test_fir_kernel_sass_contract():
+    import shutil
+    from scl_deepfake_audio_detection_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import sass_loop_stats
+    loops = {}
+    for name, ins in sass_loop_stats.functions(_lib.LIB_PATH):
+        m = re.search(r"fir_bank_kernelILi(\d)E", name)
+        if not m:
+            continue
+        text = [t for _, t, _ in ins]
+        assert not any("STL" in t or "LDL" in t for t in text), "local-memory spills in " + name
+        body = [t for _, t, _ in (sass_loop_stats.body_loop(ins) or [])]
+        loops[int(m.group(1))] = (sum("FFMA2" in t for t in body), sum("LDS.128" in t for t in body), len(body))
+    assert set(loops) == {0, 1, 2}, "one instantiation per tail mode"
+    for mode, (ffma2, lds, total) in loops.items():
+        # a 24-tap body is 240 FFMA2 + 18 LDS.128; the loop holds two (single filters) or four (LnL bank) of them
+        assert ffma2 in (480, 960) and lds == 18 * ffma2 // 240, f"tail mode {mode}: body loop changed shape ({ffma2} FFMA2, {lds} LDS.128)"
+        assert total - ffma2 - lds <= 8, f"tail mode {mode}: {total - ffma2 - lds} other instructions inside the body loop"
+    log = os.path.join(os.path.dirname(_lib.LIB_PATH), "librawboost_b200.rb_fir_bank.ptxas.log")
+    if os.path.exists(log):
+        regs = [int(r) for r in re.findall(r"Used (\d+) registers", open(log).read())]
+        assert regs and max(regs) <= 128, f"more than 128 registers: fewer than 4 CTAs of 128 threads per SM ({regs})"
