@@ -90,7 +90,7 @@ typedef struct rb_plan {
 
 /* Device workspace (bytes) that rb_* entry points need for a batch of B rows of stride ld: rb_workspace_bytes covers every
  * algo; rb_workspace_bytes_for is what one algo needs (algos 1, 2, 3 and 5 need no waveform-sized scratch at all, the
- * chained algos 4, 6, 7 one buffer, algo 8 three). */
+ * chained algos 4, 6, 7 one buffer, algo 8 two). */
 RB_API size_t rb_workspace_bytes(int B, int ld);
 RB_API size_t rb_workspace_bytes_for(int algo, int B, int ld);
 
@@ -101,7 +101,8 @@ RB_API int rb_filter_fir(const float* x, const int32_t* len, int B, int ld, cons
                   const int32_t* tap_off, float* y, void* stream);
 
 /* ---- a-2  normWav(x, always)  (RawBoost.py:20-25), batched ---------------------------------------------
- * y = x / max|x| if (always || max|x| > 1) else x. Bit-exact with numpy on float32 input. */
+ * y = x / max|x| if (always || max|x| > 1) else x. Bit-exact with numpy on float32 input (NaN propagates like np.amax).
+ * y may equal x (in place: rows that need no scaling are not rewritten at all). */
 RB_API int rb_normwav(const float* x, const int32_t* len, int B, int ld, int always, float* y, void* workspace,
                size_t workspace_bytes, void* stream);
 
@@ -111,7 +112,8 @@ RB_API int rb_lnl(const float* x, const int32_t* len, int B, int ld, const rb_pl
            size_t workspace_bytes, void* stream);
 
 /* ---- a-6  ISD_additive_noise  (RawBoost.py:73-84), arithmetic part -------------------------------------
- * y = normWav(x with y[p] = x[p] + g_sd*x[p]*f_r at the impulse positions, 0). Bit-exact on float32 input. */
+ * y = normWav(x with y[p] = x[p] + g_sd*x[p]*f_r at the impulse positions, 0); the impulses see the RAW x, whatever its
+ * peak. Bit-exact on float32 input. Positions must be unique per utterance (they are a permutation prefix). */
 RB_API int rb_isd(const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y, void* workspace,
            size_t workspace_bytes, void* stream);
 

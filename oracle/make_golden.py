@@ -3,7 +3,9 @@
 
 Run in the build container only (``/root/reference`` does not exist on the GPU box):
 
-    python oracle/make_golden.py            # rewrites tests/golden/
+    python oracle/make_golden.py            # rewrites tests/golden/rawboost_golden.*
+    python oracle/make_golden.py --multiview   # tests/golden/multiview_golden.*
+    python oracle/make_golden.py --round2      # tests/golden/round2_golden.* (edge inputs, long utterances, reverb, __getitem__)
 
 The reference's loader modules import packages that are absent here (librosa, soundfile, pydub,
 torchaudio.io, torchaudio.sox_effects); five empty stub modules are registered first so that
@@ -30,7 +32,8 @@ REF = "/root/reference"
 OUT = os.path.join(ROOT, "tests", "golden")
 
 sys.path.insert(0, ROOT)
-from oracle.rawboost_oracle import make_args, seed_for, synth_utterance  # noqa: E402
+from oracle.rawboost_oracle import (CORPUS_IDS, CORPUS_VOCODERS, corpus_wave, make_args, overscale_utterance, seed_for,  # noqa: E402
+                                    synth_utterance)
 
 
 def import_reference():
@@ -227,8 +230,128 @@ def main_multiview():
     print(f"wrote {len(arrays)} multiview arrays to {OUT}")
 
 
+def sha1_of(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def main_round2():
+    """Round-2 fixtures, all from the UNMODIFIED reference (tests/golden/round2_golden.{npz,json}):
+    inputs above full scale (every algo), float64 / all-zero / NaN inputs, utterances longer than 65536 samples
+    (what the loaders feed RawBoost before the crop, asvspoof_2019_augall_3.py:105-117), the reverb augmentor's arithmetic
+    (audio_augmentor/reverb.py:33-44) and one whole ``Dataset_for.__getitem__`` (asvspoof_2019_augall_3.py:103-146)."""
+    warnings.simplefilter("ignore", DeprecationWarning)
+    warnings.simplefilter("ignore", RuntimeWarning)  # 0/0 in normWav(zeros, 1)
+    rb, loader = import_reference()
+    args = make_args()
+    arrays, meta = {}, {"over": {}, "f64": {}, "zeros": {}, "nan": {}, "long": {}, "reverb": {}, "getitem": {}}
+
+    # ---- inputs above full scale: ISD must see the raw x (RawBoost.py:76-84), every algo -------------------------------
+    L = 16000
+    for algo in range(1, 9):
+        for u in (0, 1):
+            x = overscale_utterance(u, L)
+            np.random.seed(seed_for(50 + u))
+            y = np.asarray(loader.process_Rawboost_feature(x, 16000, args, algo))
+            key = f"over_algo{algo}_u{u}"
+            rec = summarise(y)
+            rec["stream"] = stream_digest()
+            if algo == 2:
+                rec["sha1_f32"] = sha1_of(y)  # float32 in -> float32 out: bit-exact contract
+            if algo in (2, 7, 8):
+                arrays[key] = y.astype(np.float32)
+            meta["over"][key] = rec
+    for u in (0, 1):
+        x = overscale_utterance(u, L)
+        np.random.seed(seed_for(50 + u))
+        arrays[f"over_op_isd_u{u}"] = rb.ISD_additive_noise(x, 10, 2)
+
+    # ---- float64 input (np.power keeps float64, RawBoost.py:66; ISD returns float64) --------------------------------------
+    x64 = 0.3 * np.random.RandomState(31).standard_normal(4000)
+    for algo in (1, 2, 3, 5):
+        np.random.seed(seed_for(60))
+        y = np.asarray(loader.process_Rawboost_feature(x64, 16000, args, algo))
+        arrays[f"f64_algo{algo}"] = y.astype(np.float32)
+        meta["f64"][f"f64_algo{algo}"] = {"dtype": str(y.dtype), "stream": stream_digest()}
+
+    # ---- all-zero input ---------------------------------------------------------------------------------------------------
+    z = np.zeros(1000, dtype=np.float32)
+    for algo in (1, 2, 3, 5):
+        np.random.seed(seed_for(61))
+        y = np.asarray(loader.process_Rawboost_feature(z, 16000, args, algo))
+        arrays[f"zeros_algo{algo}"] = y.astype(np.float32)
+        meta["zeros"][f"zeros_algo{algo}"] = {"nan_count": int(np.isnan(y).sum()), "stream": stream_digest()}
+    arrays["zeros_norm0"] = np.asarray(rb.normWav(z, 0))
+    arrays["zeros_norm1"] = np.asarray(rb.normWav(z, 1))  # 0/0: NaN everywhere, kept by the reference
+
+    # ---- NaN sample -------------------------------------------------------------------------------------------------------
+    xn = synth_utterance(9, 3000, True).copy()
+    xn[100] = np.nan
+    for algo in (1, 2, 3, 5):
+        np.random.seed(seed_for(62))
+        y = np.asarray(loader.process_Rawboost_feature(xn, 16000, args, algo))
+        arrays[f"nan_algo{algo}"] = y.astype(np.float32)
+        meta["nan"][f"nan_algo{algo}"] = {"nan_count": int(np.isnan(y).sum()), "stream": stream_digest()}
+    arrays["nan_norm0"] = np.asarray(rb.normWav(xn, 0))
+    arrays["nan_norm1"] = np.asarray(rb.normWav(xn, 1))
+
+    # ---- utterances longer than 65536 samples: summaries and (for the bit-exact operators) digests ------------------------
+    for Llong in (65537, 100000, 211000):
+        for loud in (0, 1):
+            x = synth_utterance(70 + loud, Llong, bool(loud))
+            if loud:
+                x = (x * 2.0).astype(np.float32)  # peak 1.8: normWav fires
+            for algo in (2, 5):
+                np.random.seed(seed_for(70))
+                y = np.asarray(loader.process_Rawboost_feature(x, 16000, args, algo))
+                rec = summarise(y)
+                rec["stream"] = stream_digest()
+                if algo == 2:
+                    rec["sha1_f32"] = sha1_of(y)
+                meta["long"][f"long_algo{algo}_L{Llong}_loud{loud}"] = rec
+            for always in (0, 1):
+                meta["long"][f"long_norm{always}_L{Llong}_loud{loud}"] = {"sha1_f32": sha1_of(rb.normWav(x, always))}
+
+    # ---- reverb: ReverbAugmentor.transform on a synthetic impulse response -------------------------------------------------
+    import datautils.audio_augmentor.reverb as ref_reverb
+    captured = {}
+    rir = (np.exp(-np.arange(3000) / 400.0) * np.random.RandomState(5).standard_normal(3000)).astype(np.float32)
+    ref_reverb.librosa.load = lambda path, sr=None, **kw: (rir, sr)
+    ref_reverb.librosa_to_pydub = lambda data, sr=16000: captured.__setitem__("y", np.array(data)) or "segment"
+    aug = ref_reverb.ReverbAugmentor.__new__(ref_reverb.ReverbAugmentor)  # __init__ lists a corpus directory; not needed here
+    aug.sr, aug.rir_file = 16000, "synthetic.wav"
+    for tag, data in (("speech", synth_utterance(80, 20000, False)), ("loud", synth_utterance(81, 7001, True))):
+        aug.data = data
+        aug.transform()
+        arrays[f"reverb_{tag}"] = captured["y"].astype(np.float32)
+        meta["reverb"][f"reverb_{tag}"] = {"dtype": str(captured["y"].dtype), "len": int(captured["y"].shape[0]),
+                                           "peak": float(np.abs(captured["y"]).max())}
+    arrays["reverb_rir"] = rir
+
+    # ---- one whole Dataset item through the reference's own __getitem__ ---------------------------------------------------
+    ids, vocoders = list(CORPUS_IDS), list(CORPUS_VOCODERS)
+    loader.librosa.load = lambda path, sr=None, mono=True, **kw: (corpus_wave(path), sr)
+    ds = loader.Dataset_for(make_args(), ids, {}, "/data", vocoders=vocoders, augmentation_methods=["RawBoost12"],
+                            num_additional_real=2, trim_length=12000, online_aug=True, aug_dir="", repeat_pad=True)
+    for idx in (0, 3):
+        np.random.seed(8000 + idx)
+        utt, data, label = ds[idx]
+        arrays[f"getitem{idx}_data"] = data.numpy().astype(np.float32)
+        arrays[f"getitem{idx}_label"] = label.numpy().astype(np.float32)
+        meta["getitem"][f"getitem{idx}"] = {"utt": utt, "seed": 8000 + idx, "shape": list(data.shape), "trim_length": 12000,
+                                            "num_additional_real": 2, "vocoders": vocoders, "stream": stream_digest()}
+    meta["getitem"]["ids"] = ids
+
+    np.savez_compressed(os.path.join(OUT, "round2_golden.npz"), **arrays)
+    with open(os.path.join(OUT, "round2_golden.json"), "w") as f:
+        json.dump(meta, f, indent=1, sort_keys=True)
+    size = os.path.getsize(os.path.join(OUT, "round2_golden.npz"))
+    print(f"wrote {len(arrays)} round-2 arrays ({size/1e6:.2f} MB) to {OUT}")
+
+
 if __name__ == "__main__":
     if "--multiview" in sys.argv:
         main_multiview()
+    elif "--round2" in sys.argv:
+        main_round2()
     else:
         main()

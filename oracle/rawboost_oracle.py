@@ -35,7 +35,7 @@ __all__ = [
     "rand_range", "norm_wav", "draw_notch_taps", "filter_fir", "filter_fir_closed_form",
     "LnLPlan", "ISDPlan", "SSIPlan", "draw_lnl_plan", "apply_lnl", "draw_isd_plan", "apply_isd",
     "draw_ssi_plan", "apply_ssi", "lnl", "isd", "ssi", "process", "DEFAULT_ARGS", "make_args",
-    "synth_utterance", "seed_for",
+    "synth_utterance", "seed_for", "dataset_item", "overscale_utterance", "corpus_wave", "CORPUS_IDS", "CORPUS_VOCODERS",
 ]
 
 
@@ -306,6 +306,55 @@ def reverb_convolve(data, rir_data):
     reverberate = np.convolve(np.asarray(data, dtype=np.float64), np.asarray(rir_data, dtype=np.float64))
     reverberate /= np.max(np.abs(reverberate))
     return reverberate
+
+
+def dataset_item(idx, list_ids, load_audio, args, vocoders, num_additional_real, trim_length, sr=16000, repeat_pad=True,
+                 bonafide_dir="/data/bonafide", vocoded_dir="/data/vocoded"):
+    """``Dataset_for.__getitem__`` with ``augmentation_methods == ['RawBoost12']``, ``online_aug`` on
+    (/root/reference/datautils/asvspoof_2019_augall_3.py:103-146). Draw order on the global stream: RawBoost (algo 5) on
+    every vocoded copy, RawBoost on the anchor, ``np.random.choice`` of the additional bona fide utterances, the shared crop.
+    View order: anchor, augmented anchor, additional, vocoded, augmented vocoded. Returns (utt id, [length, V] float32,
+    labels float32): 1 for the anchor / positives, 0 for everything vocoded."""
+    import os
+    anchor_path = os.path.join(bonafide_dir, list_ids[idx])
+    anchor = load_audio(anchor_path)
+    vocoded, aug_vocoded = [], []
+    for v in vocoders:
+        w = load_audio(os.path.join(vocoded_dir, v + "_" + list_ids[idx]))
+        vocoded.append(np.expand_dims(w, 1))
+        aug_vocoded.append(np.expand_dims(process(w, sr, args, 5), 1))
+    augmented = [np.expand_dims(process(anchor, sr, args, 5), 1)]
+    others = list(range(len(list_ids)))
+    others.remove(idx)
+    extra_idx = np.random.choice(others, num_additional_real, replace=False)
+    extra = [np.expand_dims(load_audio(os.path.join(bonafide_dir, list_ids[i])), 1) for i in extra_idx]
+    views = [np.expand_dims(anchor, 1)] + augmented + extra + vocoded + aug_vocoded
+    out = batch_pad_for_multiview(views, sr, trim_length, random_trim_nosil=True, repeat_pad=repeat_pad)
+    data = np.concatenate(out, axis=1).astype(np.float32)
+    label = np.array([1] * (len(augmented) + len(extra) + 1) + [0] * (2 * len(vocoders)), dtype=np.float32)
+    return list_ids[idx], data, label
+
+
+def overscale_utterance(u: int, length: int) -> np.ndarray:
+    """Input above full scale (peak ~2.5): the case in which it matters that ISD sees the raw x before normWav."""
+    return (2.5 * np.random.RandomState(777 + u).uniform(-1, 1, length)).astype(np.float32)
+
+
+CORPUS_IDS = [f"utt{k}.wav" for k in range(6)]
+CORPUS_VOCODERS = ["hifigan", "hn-sinc-nsf-hifi", "waveglow"]
+
+
+def corpus_wave(path: str) -> np.ndarray:
+    """The synthetic stand-in for ``librosa.load`` used by the ``__getitem__`` fixtures: ``<dir>/utt<k>.wav`` and
+    ``<dir>/<vocoder>_utt<k>.wav`` map to seeded waveforms of slightly different lengths."""
+    import os
+    name = os.path.basename(path)
+    for vi, v in enumerate(CORPUS_VOCODERS):
+        if name.startswith(v + "_"):
+            k = CORPUS_IDS.index(name[len(v) + 1:])
+            return synth_utterance(900 + 10 * k + vi + 1, 15000 + 111 * k + 13 * vi, bool(vi % 2))
+    k = CORPUS_IDS.index(name)
+    return synth_utterance(900 + 10 * k, 15000 + 111 * k, False)
 
 
 class _Args:

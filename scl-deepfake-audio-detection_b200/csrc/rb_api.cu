@@ -56,20 +56,17 @@ inline int mask_ld_for(int ld) { return (int)align_up((size_t)ld / 32 + 2, 4); }
 // Device workspace layout for one batch.
 struct Workspace {
   float* stats_a;
-  float* stats_b;
-  UttParams* params;
   uint32_t* counters;  // per-utterance tile arrival counters of the fused FIR tail
   uint32_t* mask;
   int mask_ld;
   float* buf1;  // intermediate waveform of the chained algos 4, 6, 7, 8
   float* buf2;  // second branch of algo 8
-  float* buf0;  // sum of the two branches of algo 8
   size_t bytes;
 };
 
 // Waveform-sized scratch buffers an algo needs: the single-operator algos (1, 2, 3) and the fused LnL -> ISD (5) write into
 // the output buffer itself; the chains 4, 6, 7 hold one intermediate waveform; algo 8 two branches and their sum.
-inline int scratch_waveforms(int algo) { return algo == 8 ? 3 : (algo == 4 || algo == 6 || algo == 7) ? 1 : 0; }
+inline int scratch_waveforms(int algo) { return algo == 8 ? 2 : (algo == 4 || algo == 6 || algo == 7) ? 1 : 0; }
 
 Workspace carve(void* base, int B, int ld, int nbuf) {
   Workspace w;
@@ -82,14 +79,11 @@ Workspace carve(void* base, int B, int ld, int nbuf) {
     return r;
   };
   w.stats_a = (float*)take((size_t)B * ntiles * kStatN * sizeof(float));
-  w.stats_b = (float*)take((size_t)B * ntiles * kStatN * sizeof(float));
-  w.params = (UttParams*)take((size_t)B * sizeof(UttParams));
   w.counters = (uint32_t*)take((size_t)B * sizeof(uint32_t));
   w.mask_ld = mask_ld_for(ld);
   w.mask = (uint32_t*)take((size_t)B * w.mask_ld * sizeof(uint32_t));
   w.buf1 = nbuf >= 1 ? (float*)take((size_t)B * ld * sizeof(float)) : nullptr;
   w.buf2 = nbuf >= 2 ? (float*)take((size_t)B * ld * sizeof(float)) : nullptr;
-  w.buf0 = nbuf >= 3 ? (float*)take((size_t)B * ld * sizeof(float)) : nullptr;
   w.bytes = off;
   return w;
 }
@@ -138,30 +132,14 @@ int do_lnl(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
                          with_isd ? w.mask : nullptr, w.mask_ld, tail, st);
 }
 
-// ISD on an existing waveform: x -> out (out != x)
+// ISD on an existing waveform: x -> out. Mask build + ONE streaming launch (impulses, peak and the conditional rescale happen
+// in its per-utterance tail). The input is NOT normalised first: the reference applies the impulses to the raw x
+// (RawBoost.py:76-84) and only then normWav(y, 0).
 int do_isd(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl, float* out, const Workspace& w, cudaStream_t st) {
   if (!pl || !pl->isd_off || !pl->isd_idx || !pl->isd_fr) return RB_ERR_PLAN;
-  {  // one kernel, one pass over HBM; the multi-pass composition below only serves utterances whose mask exceeds shared memory
-    const int rc = launch_isd_fused(x, len, B, ld, 0, pl->isd_off, pl->isd_idx, pl->isd_fr, pl->g_sd, out, st);
-    if (rc != RB_ERR_UNSUPPORTED) return rc;
-  }
   RB_TRY(launch_mask_build(pl->isd_off, pl->isd_idx, len, B, w.mask, w.mask_ld, st));
-  RB_TRY(launch_dense_stats(x, len, B, ld, w.stats_a, w.mask, w.mask_ld, st));
-  FinalizeArgs fa{};
-  fa.stats = w.stats_a;
-  fa.ntiles = tiles_for(ld);
-  fa.len = len;
-  fa.raw = x;
-  fa.ld = ld;
-  fa.isd_off = pl->isd_off;
-  fa.isd_idx = pl->isd_idx;
-  fa.isd_fr = pl->isd_fr;
-  fa.g_sd = pl->g_sd;
-  fa.out = w.params;
-  RB_TRY(launch_finalize(fa, B, st));
-  RB_TRY(launch_apply_affine(x, len, B, ld, w.params, out, st));
-  RB_TRY(launch_isd_scatter(x, len, B, ld, pl->isd_off, pl->isd_idx, pl->isd_fr, pl->g_sd, w.params, out, st));
-  return RB_OK;
+  return launch_norm_stream(x, nullptr, len, B, ld, 0, w.mask, w.mask_ld, pl->isd_off, pl->isd_idx, pl->isd_fr, pl->g_sd, out,
+                            (uint32_t*)w.stats_a, w.counters, st);
 }
 
 // SSI: x -> out (out must not alias x: the tail of one utterance reads x while other tiles still compute statistics of it).
@@ -179,21 +157,11 @@ int do_ssi(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
   return launch_fir_bank(pl->ssi_noise, len, B, ld, pl->ssi_taps, pl->ssi_tap_off, 1, 1, 0, out, w.stats_a, nullptr, 0, tail, st);
 }
 
-// normWav: x -> out
-int do_normwav(const float* x, const int32_t* len, int B, int ld, int always, float* out, const Workspace& w, cudaStream_t st) {
-  const int rc = launch_isd_fused(x, len, B, ld, always, nullptr, nullptr, nullptr, 0.f, out, st);
-  if (rc != RB_ERR_UNSUPPORTED) return rc;
-  RB_TRY(launch_dense_stats(x, len, B, ld, w.stats_a, nullptr, 0, st));
-  FinalizeArgs fa{};
-  fa.stats = w.stats_a;
-  fa.ntiles = tiles_for(ld);
-  fa.len = len;
-  fa.always = always ? 1 : 0;
-  fa.raw = x;
-  fa.ld = ld;
-  fa.out = w.params;
-  RB_TRY(launch_finalize(fa, B, st));
-  return launch_apply_affine(x, len, B, ld, w.params, out, st);
+// normWav: x -> out (out may equal x), or with `add`: normWav(x + add) -> out
+int do_normwav(const float* x, const float* add, const int32_t* len, int B, int ld, int always, float* out, const Workspace& w,
+               cudaStream_t st) {
+  return launch_norm_stream(x, add, len, B, ld, always, nullptr, 0, nullptr, nullptr, nullptr, 0.f, out, (uint32_t*)w.stats_a,
+                            w.counters, st);
 }
 
 }  // namespace
@@ -222,7 +190,7 @@ int rb_abi_version(void) { return RB_ABI_VERSION; }
 
 size_t rb_workspace_bytes(int B, int ld) {
   if (B <= 0 || ld <= 0) return 0;
-  return carve(nullptr, B, ld, 3).bytes;
+  return carve(nullptr, B, ld, 2).bytes;
 }
 
 size_t rb_workspace_bytes_for(int algo, int B, int ld) {
@@ -261,7 +229,7 @@ int rb_filter_fir(const float* x, const int32_t* len, int B, int ld, const float
                   void* stream) {
   RB_TRY(check_batch(x, len, B, ld, y));
   if (B == 0 || ld == 0) return RB_OK;
-  if (!taps || !tap_off) return RB_ERR_INVALID_ARG;
+  if (!taps || !tap_off || x == y) return RB_ERR_INVALID_ARG;  // not in-place safe: a tile reads its neighbours' samples
   return launch_fir_bank(x, len, B, ld, taps, tap_off, 1, 1, 0, y, nullptr, nullptr, 0, FirTail(), (cudaStream_t)stream);
 }
 
@@ -271,7 +239,7 @@ int rb_normwav(const float* x, const int32_t* len, int B, int ld, int always, fl
   if (B == 0 || ld == 0) return RB_OK;
   Workspace w;
   RB_TRY(check_ws(workspace, workspace_bytes, B, ld, 0, &w));
-  return do_normwav(x, len, B, ld, always, y, w, (cudaStream_t)stream);
+  return do_normwav(x, nullptr, len, B, ld, always, y, w, (cudaStream_t)stream);
 }
 
 int rb_lnl(const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y, void* workspace,
@@ -316,8 +284,7 @@ int rb_process(int algo, const float* x, const int32_t* len, int B, int ld, cons
     case 8:
       RB_TRY(do_lnl(x, len, B, ld, plan, false, w.buf1, w, st));
       RB_TRY(do_isd(x, len, B, ld, plan, w.buf2, w, st));
-      RB_TRY(launch_apply_sum(w.buf1, w.buf2, len, B, ld, w.buf0, st));
-      return do_normwav(w.buf0, len, B, ld, 0, y, w, st);
+      return do_normwav(w.buf1, w.buf2, len, B, ld, 0, y, w, st);  // the sum of the branches is formed inside the streaming pass
   }
   return RB_ERR_INVALID_ARG;
 }

@@ -1,9 +1,21 @@
-// rb_dense.cu -- the HBM-bound passes around the FIR bank: ISD impulse mask, per-tile statistics, the
-// per-utterance finalisers (mean / max-abs / norms via warp shuffles), the dense apply pass and the sparse
-// impulsive-noise scatter.
+// rb_dense.cu -- the HBM-bound operators: normWav, the stand-alone impulsive noise (ISD) and the two-branch sum of algo 8.
 //
 // Reference arithmetic being restated (file:line under /root/reference/datautils/RawBoost.py):
-//   normWav 20-25, LnL tail (mean removal + normWav) 67-68, ISD 76-84, SSI tail 93-96.
+//   normWav 20-25:  m = max|x|;  x / m  if (always or m > 1) else x
+//   ISD     76-84:  y = copy(x); y[p] = x[p] + g_sd * x[p] * f_r;  normWav(y, 0)          (x itself is NOT normalised first)
+//   algo 8  (asvspoof_2019_augall_3.py:425-432):  normWav(LnL(x) + ISD(x), 0)
+//
+// Design: normWav is the identity unless the peak exceeds 1 (or `always`), so nothing has to wait for the peak. One streaming
+// pass over (utterance, 4096-sample tile) CTAs copies every tile to the output at copy speed while it takes the tile's peak;
+// a per-utterance arrival counter elects the CTA that finishes an utterance's last tile, and only that CTA
+//   * applies the utterance's impulses (gathering x[p] and scattering y[p] through L2, where the row was streamed a moment ago),
+//   * folds their magnitudes into the peak, and
+//   * only if the reference would divide (peak > 1 or `always`) rescales the row in place while it is still L2-resident.
+// HBM therefore sees each sample once in and once out; many small CTAs per SM (8 x 256 threads, 16 KB in flight each) keep the
+// memory pipeline full, where the previous one-CTA-per-utterance kernel (load everything -> reduce -> store) sat at 35-40 %.
+// All reductions are maxima of |.|, taken on the bit patterns (for non-negative floats the unsigned order is the numeric
+// order and every NaN sorts above +inf), so the result is independent of the reduction order, bit-exact against numpy, and
+// NaN propagates like np.amax.
 #include "rb_common.cuh"
 #include "rb_dense.cuh"
 #include "rb_finalize.cuh"
@@ -12,12 +24,39 @@ namespace rb {
 
 namespace {
 
-constexpr int kSparseChunks = 8;  // CTAs per utterance for the impulse kernels (grid-stride inside)
-
 // ---- ISD impulse bit mask: bit p of row u set iff p is an impulse position of utterance u ---------
-__global__ void __launch_bounds__(256)
+// One CTA per utterance assembles the row in shared memory (no global atomics, no memset) and writes it out once.
+constexpr int kMaskThreads = 256;
+constexpr int kMaskSmemWords = 12 * 1024;  // rows of up to 393216 samples; longer ones take the global-atomic kernel
+
+__global__ void __launch_bounds__(kMaskThreads)
 mask_build_kernel(const int32_t* __restrict__ isd_off, const int32_t* __restrict__ isd_idx, const int32_t* __restrict__ len_arr,
                   uint32_t* __restrict__ mask, int mask_ld) {
+  extern __shared__ uint32_t smask[];
+  const int u = blockIdx.x, tid = threadIdx.x;
+  const int beg = isd_off[u], end = isd_off[u + 1], len = len_arr[u];
+  for (int w = tid; w < mask_ld; w += kMaskThreads) smask[w] = 0u;
+  __syncthreads();
+  constexpr int kU = 4;  // positions in flight per thread
+  for (int i0 = beg + tid; i0 < end; i0 += kU * kMaskThreads) {
+    int p[kU];
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      const int i = i0 + k * kMaskThreads;
+      p[k] = (i < end) ? __ldg(isd_idx + i) : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < kU; ++k)
+      if (p[k] >= 0 && p[k] < len) atomicOr(smask + (p[k] >> 5), 1u << (p[k] & 31));
+  }
+  __syncthreads();
+  uint32_t* mrow = mask + (size_t)u * mask_ld;
+  for (int w = tid; w < mask_ld; w += kMaskThreads) mrow[w] = smask[w];
+}
+
+__global__ void __launch_bounds__(256)
+mask_build_global_kernel(const int32_t* __restrict__ isd_off, const int32_t* __restrict__ isd_idx, const int32_t* __restrict__ len_arr,
+                         uint32_t* __restrict__ mask, int mask_ld) {
   const int u = blockIdx.y;
   const int beg = isd_off[u], end = isd_off[u + 1], len = len_arr[u];
   uint32_t* mrow = mask + (size_t)u * mask_ld;
@@ -27,438 +66,181 @@ mask_build_kernel(const int32_t* __restrict__ isd_off, const int32_t* __restrict
   }
 }
 
-// ---- per-tile statistics of a waveform batch (same layout as the FIR-bank epilogue) ---------------
-__global__ void __launch_bounds__(kThreads)
-dense_stats_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, float* __restrict__ stats,
-                   const uint32_t* __restrict__ mask, int mask_ld) {
-  __shared__ float red[4][kStatN];
-  const int u = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
-  const int len = len_arr[u];
-  const int tile0 = tile * kTile;
-  float* st_out = stats + ((size_t)u * gridDim.x + tile) * kStatN;
-  float s_sum = 0.f, s_sq = 0.f, s_min = INFINITY, s_max = -INFINITY, s_minu = INFINITY, s_maxu = -INFINITY;
-  if (tile0 < len) {
-    const float* row = x + (size_t)u * ld;
-    const uint32_t* mrow = mask ? mask + (size_t)u * mask_ld : nullptr;
-    float4 v[kR / 4];
-    uint32_t hit[kR / 4];
-#pragma unroll
-    for (int k = 0; k < kR / 4; ++k) {  // issue all loads first
-      const int p = tile0 + 4 * (k * kThreads + tid);
-      if (p + 3 < len) {
-        v[k] = __ldg(reinterpret_cast<const float4*>(row + p));
-      } else {
-        v[k].x = (p + 0 < len) ? __ldg(row + p + 0) : 0.f;
-        v[k].y = (p + 1 < len) ? __ldg(row + p + 1) : 0.f;
-        v[k].z = (p + 2 < len) ? __ldg(row + p + 2) : 0.f;
-        v[k].w = (p + 3 < len) ? __ldg(row + p + 3) : 0.f;
-      }
-      hit[k] = (mrow && p < len) ? ((__ldg(mrow + (p >> 5)) >> (p & 31)) & 0xFu) : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < kR / 4; ++k) {
-      const int p = tile0 + 4 * (k * kThreads + tid);
-      const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (p + q < len) {
-          s_sum += e[q];
-          s_sq = fmaf(e[q], e[q], s_sq);
-          s_min = fminf(s_min, e[q]);
-          s_max = fmaxf(s_max, e[q]);
-          if (!((hit[k] >> q) & 1u)) {
-            s_minu = fminf(s_minu, e[q]);
-            s_maxu = fmaxf(s_maxu, e[q]);
-          }
-        }
-      }
-    }
-  }
-  s_sum = warp_sum(s_sum);
-  s_sq = warp_sum(s_sq);
-  s_min = warp_min(s_min);
-  s_max = warp_max(s_max);
-  s_minu = warp_min(s_minu);
-  s_maxu = warp_max(s_maxu);
-  const int warp = tid >> 5, lane = tid & 31;
-  if (lane == 0) {
-    red[warp][S_SUM] = s_sum;
-    red[warp][S_SUMSQ] = s_sq;
-    red[warp][S_MIN] = s_min;
-    red[warp][S_MAX] = s_max;
-    red[warp][S_MINU] = s_minu;
-    red[warp][S_MAXU] = s_maxu;
-  }
+// ---- the streaming pass ---------------------------------------------------------------------------------------------------
+#ifndef RB_STREAM_THREADS
+#define RB_STREAM_THREADS 256
+#endif
+#ifndef RB_STREAM_CHUNKS
+#define RB_STREAM_CHUNKS 4
+#endif
+constexpr int kSThreads = RB_STREAM_THREADS;     // threads per CTA
+constexpr int kSU = RB_STREAM_CHUNKS;            // float4 chunks per thread, all in flight at once
+constexpr int kSTile = kSThreads * kSU * 4;      // samples per CTA (4096)
+
+__device__ __forceinline__ uint32_t abs_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+
+// max over the CTA of a uint32 held by every thread; returned in every thread. `scratch` holds one word per warp.
+__device__ __forceinline__ uint32_t block_umax(uint32_t v, uint32_t* scratch) {
+  const int tid = threadIdx.x;
+  v = __reduce_max_sync(0xffffffffu, v);
+  __syncthreads();  // scratch may still be read by a previous call
+  if ((tid & 31) == 0) scratch[tid >> 5] = v;
   __syncthreads();
-  if (tid < kStatN) {
-    float r;
-    if (tid == S_SUM || tid == S_SUMSQ) r = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
-    else if (tid == S_MIN || tid == S_MINU) r = fminf(fminf(red[0][tid], red[1][tid]), fminf(red[2][tid], red[3][tid]));
-    else if (tid == S_MAX || tid == S_MAXU) r = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid]));
-    else r = 0.f;
-    st_out[tid] = r;
-  }
+  uint32_t r = scratch[0];
+#pragma unroll
+  for (int w = 1; w < kSThreads / 32; ++w) r = max(r, scratch[w]);
+  return r;
 }
 
-// ---- per-utterance finaliser: one CTA per utterance (arithmetic in rb_finalize.cuh) ----------------------------------------
-__global__ void __launch_bounds__(kThreads)
-finalize_kernel(FinalizeArgs a) {
-  const int u = blockIdx.x;
-  const int n = a.len[u];
-  const bool with_isd = a.isd_off != nullptr;
-  const UttParams p = finalize_block(a.stats + (size_t)u * a.ntiles * kStatN, a.ntiles, n, a.center, a.always,
-                                     a.raw + (size_t)u * a.ld, a.isd_idx, a.isd_fr, with_isd ? a.isd_off[u] : 0,
-                                     with_isd ? a.isd_off[u + 1] : 0, with_isd, a.g_sd);
-  if (threadIdx.x == 0) a.out[u] = p;
-}
+struct StreamArgs {
+  const float* a;            // [B][ld] input
+  const float* b;            // [B][ld] second addend (kSum) or nullptr
+  const int32_t* len;        // [B]
+  int ld;
+  int ntiles;                // tiles per row = ceil(ld / kSTile)
+  int always;                // normWav(., 1)
+  const uint32_t* mask;      // [B][mask_ld] impulse bit mask (kIsd)
+  int mask_ld;
+  const int32_t* isd_off;    // kIsd: impulses of utterance u are [off[u], off[u+1])
+  const int32_t* isd_idx;
+  const double* isd_fr;
+  float g_sd;
+  float* out;                // [B][ld]; may equal a when !kSum (in place: the copy is skipped)
+  uint32_t* tile_peak;       // [B][ntiles] bit patterns of the per-tile peaks
+  uint32_t* counters;        // [B] arrival counters, zero on entry, left zero
+};
 
-// ---- SSI scale (RawBoost.py:95) -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
-ssi_finalize_kernel(const float* __restrict__ stats_x, const float* __restrict__ stats_n, int ntiles,
-                    const float* __restrict__ snr_db, UttParams* __restrict__ out) {
-  const int u = blockIdx.x;
-  const float scale = ssi_scale_block(stats_x + (size_t)u * ntiles * kStatN, S_SUMSQ, stats_n + (size_t)u * ntiles * kStatN, ntiles,
-                                      snr_db[u]);
-  if (threadIdx.x == 0) {
-    UttParams p;
-    p.sub = 0.f;
-    p.div1 = 1.f;
-    p.div2 = 1.f;
-    p.scale = scale;
-    out[u] = p;
-  }
-}
-
-// ---- dense elementwise passes ---------------------------------------------------------------------
-enum { APPLY_AFFINE = 0, APPLY_SSI = 1, APPLY_SUM = 2 };
-
-template <int MODE>
-__global__ void __launch_bounds__(kThreads)
-apply_kernel(const float* __restrict__ a, const float* __restrict__ b, const int32_t* __restrict__ len_arr, int ld,
-             const UttParams* __restrict__ params, float* __restrict__ out) {
-  const int u = blockIdx.y, tid = threadIdx.x;
-  const int len = len_arr[u];
-  const int tile0 = blockIdx.x * kTile;
+#ifndef RB_STREAM_MIN_BLOCKS
+#define RB_STREAM_MIN_BLOCKS 6
+#endif
+template <bool kIsd, bool kSum>
+__global__ void __launch_bounds__(kSThreads, RB_STREAM_MIN_BLOCKS)
+norm_stream_kernel(const StreamArgs s) {
+  __shared__ uint32_t scratch[kSThreads / 32];
+  __shared__ int s_last;
+  const int u = blockIdx.x / s.ntiles, tile = blockIdx.x - u * s.ntiles;
+  const int tid = threadIdx.x;
+  const int len = s.len[u];
+  const int tile0 = tile * kSTile;
   if (tile0 >= len) return;
-  UttParams pr;
-  if (MODE != APPLY_SUM) pr = params[u];
-  const float* ra = a + (size_t)u * ld;
-  const float* rb_ = (MODE != APPLY_AFFINE) ? b + (size_t)u * ld : nullptr;
-  float* ro = out + (size_t)u * ld;
-  float4 va[kR / 4], vb[kR / 4];
+  const float* ra = s.a + (size_t)u * s.ld;
+  const float* rb_ = kSum ? s.b + (size_t)u * s.ld : nullptr;
+  float* ro = s.out + (size_t)u * s.ld;
+  const bool copy = kSum || (ro != ra);
+
+  float4 v[kSU];
+  uint32_t hit[kSU];
 #pragma unroll
-  for (int k = 0; k < kR / 4; ++k) {
-    const int p = tile0 + 4 * (k * kThreads + tid);
+  for (int k = 0; k < kSU; ++k) {  // every load of the tile is issued before the first use
+    const int p = tile0 + 4 * (k * kSThreads + tid);
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    hit[k] = 0u;
     if (p + 3 < len) {
-      va[k] = __ldg(reinterpret_cast<const float4*>(ra + p));
-      if (MODE != APPLY_AFFINE) vb[k] = __ldg(reinterpret_cast<const float4*>(rb_ + p));
-    } else {
-      float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f};
+      v[k] = __ldg(reinterpret_cast<const float4*>(ra + p));
+      if (kSum) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(rb_ + p));
+        v[k] = make_float4(__fadd_rn(v[k].x, w.x), __fadd_rn(v[k].y, w.y), __fadd_rn(v[k].z, w.z), __fadd_rn(v[k].w, w.w));
+      }
+    } else if (p < len) {  // the ragged last chunk; zeros beyond the end are neutral for the peak
+      float e[4] = {0.f, 0.f, 0.f, 0.f};
       for (int q = 0; q < 4; ++q)
-        if (p + q < len) {
-          ta[q] = __ldg(ra + p + q);
-          if (MODE != APPLY_AFFINE) tb[q] = __ldg(rb_ + p + q);
-        }
-      va[k] = make_float4(ta[0], ta[1], ta[2], ta[3]);
-      vb[k] = make_float4(tb[0], tb[1], tb[2], tb[3]);
+        if (p + q < len) e[q] = kSum ? __fadd_rn(__ldg(ra + p + q), __ldg(rb_ + p + q)) : __ldg(ra + p + q);
+      v[k] = make_float4(e[0], e[1], e[2], e[3]);
     }
+    if (kIsd && p < len) hit[k] = (__ldg(s.mask + (size_t)u * s.mask_ld + (p >> 5)) >> (p & 31)) & 0xFu;
   }
+  uint32_t m = 0u;  // peak of the samples no impulse touches
 #pragma unroll
-  for (int k = 0; k < kR / 4; ++k) {
-    const int p = tile0 + 4 * (k * kThreads + tid);
-    float ea[4] = {va[k].x, va[k].y, va[k].z, va[k].w};
-    float eb[4] = {vb[k].x, vb[k].y, vb[k].z, vb[k].w};
-    float r[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (MODE == APPLY_AFFINE) r[q] = affine_value(ea[q], pr);
-      else if (MODE == APPLY_SSI) r[q] = __fmaf_rn(eb[q], pr.scale, ea[q]);
-      else r[q] = __fadd_rn(ea[q], eb[q]);
-    }
-    if (p + 3 < len) {
-      reinterpret_cast<float4*>(ro + p)[0] = make_float4(r[0], r[1], r[2], r[3]);
-    } else {
-      for (int q = 0; q < 4; ++q)
-        if (p + q < len) ro[p + q] = r[q];
-    }
-  }
-}
-
-// ---- sparse impulsive-noise scatter: overwrites out[p] at the impulse positions ---------------------
-__global__ void __launch_bounds__(256)
-isd_scatter_kernel(const float* __restrict__ raw, const int32_t* __restrict__ len_arr, int ld, const int32_t* __restrict__ isd_off,
-                   const int32_t* __restrict__ isd_idx, const double* __restrict__ isd_fr, float g_sd,
-                   const UttParams* __restrict__ params, float* __restrict__ out) {
-  const int u = blockIdx.y;
-  const int len = len_arr[u];
-  const UttParams pr = params[u];
-  const float* row = raw + (size_t)u * ld;
-  float* ro = out + (size_t)u * ld;
-  for (int i = isd_off[u] + blockIdx.x * 256 + threadIdx.x; i < isd_off[u + 1]; i += gridDim.x * 256) {
-    const int p = isd_idx[i];
-    if (p >= 0 && p < len) {
-      const float v = __fdiv_rn(__fsub_rn(row[p], pr.sub), pr.div1);
-      ro[p] = __fdiv_rn(isd_value(v, g_sd, isd_fr[i]), pr.div2);
-    }
-  }
-}
-
-// ---- ISD / normWav in one kernel, one CTA per utterance -------------------------------------------------------------------
-// normWav(x, always) followed (optionally) by the impulse scatter and its normWav(., 0) (RawBoost.py:20-25, 76-84). Every
-// quantity is a max, so the result does not depend on the reduction order.
-// The peaks need the whole utterance before the first sample can be written, and 64600 floats do not fit one SM's shared
-// memory next to a second CTA. So thread t owns float4 chunks t, t+512, ...: the first kParkSmem of them are parked in shared
-// memory (96 KB) and the next kParkRegs in registers while the peaks are taken; only the chunks beyond (half of a 64600-sample
-// utterance) are read a second time, last-read first, while they are still in L2 (2 CTAs/SM x 148 SMs x 126 KB = 37 MB of
-// re-read footprint). HBM traffic is therefore close to the algorithmic read-once / write-once; two CTAs per SM overlap one
-// utterance's load phase with the other's store phase. The impulse bit mask lives in shared memory.
-// (the RB_ISD_* macros exist for variant experiments: scripts/gpu_variants.sh style builds with RB_EXTRA_FLAGS)
-#ifndef RB_ISD_THREADS
-#define RB_ISD_THREADS 512
-#endif
-#ifndef RB_ISD_PARK_SMEM
-#define RB_ISD_PARK_SMEM 9
-#endif
-#ifndef RB_ISD_PARK_REGS
-#define RB_ISD_PARK_REGS 4
-#endif
-#ifndef RB_ISD_OVER_U
-#define RB_ISD_OVER_U 6
-#endif
-#ifndef RB_ISD_MIN_BLOCKS
-#define RB_ISD_MIN_BLOCKS 2
-#endif
-constexpr int kFusedThreads = RB_ISD_THREADS;
-constexpr int kParkSmem = RB_ISD_PARK_SMEM;   // chunks per thread parked in shared memory
-constexpr int kParkRegs = RB_ISD_PARK_REGS;   // chunks per thread kept in registers
-constexpr int kParkChunks = (kParkSmem + kParkRegs) * kFusedThreads;  // float4 chunks resident on chip (32768 samples)
-constexpr int kOverU = RB_ISD_OVER_U;         // overflow chunks in flight per thread
-#ifndef RB_ISD_IMP_U
-#define RB_ISD_IMP_U 4
-#endif
-constexpr int kImpU = RB_ISD_IMP_U;           // impulses in flight per thread in the mask / gather / scatter loops
-constexpr int kStash = 6528;   // impulse values kept in shared memory between the peak and the scatter (P = 10 % of 64600 = 6460)
-
-__global__ void __launch_bounds__(kFusedThreads, RB_ISD_MIN_BLOCKS)
-isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, int always,
-                 const int32_t* __restrict__ isd_off, const int32_t* __restrict__ isd_idx, const double* __restrict__ isd_fr,
-                 float g_sd, float* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char dynsm[];
-  float4* park = reinterpret_cast<float4*>(dynsm);                                                  // [kParkSmem][512]
-  float* stash = reinterpret_cast<float*>(dynsm + (size_t)kParkSmem * kFusedThreads * 16);          // [kStash]     } only with
-  uint32_t* smask = reinterpret_cast<uint32_t*>(stash + kStash);                                    // [ceil(len/32)] } impulses
-  __shared__ float red[kFusedThreads / 32][2];
-  __shared__ float bc[3];
-  const int u = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int len = len_arr[u];
-  if (len <= 0) return;
-  const float* row = x + (size_t)u * ld;
-  float* orow = out + (size_t)u * ld;
-  const bool with_isd = isd_off != nullptr;
-  const int ibeg = with_isd ? isd_off[u] : 0, iend = with_isd ? isd_off[u + 1] : 0;
-  const int nchunk = (len + 3) >> 2;
-
-  // streaming loads go around L1 (ld.global.cg): with ~100 KB of shared memory per CTA the L1 that is left is far smaller
-  // than the ~100 KB per CTA kept in flight here
-  auto load_chunk = [&](int c) {  // float4 chunk c of the row, zero beyond the end
-    const int p = 4 * c;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p + 3 < len) {
-      v = __ldcg(reinterpret_cast<const float4*>(row + p));
-    } else if (p < len) {
-      v.x = __ldcg(row + p);
-      if (p + 1 < len) v.y = __ldcg(row + p + 1);
-      if (p + 2 < len) v.z = __ldcg(row + p + 2);
-    }
-    return v;
-  };
-  // Everything that fits on chip is requested at once: the parked chunks go global -> shared by cp.async (no registers
-  // involved, so all nine per thread are in flight together), the kept chunks into registers. The impulse mask is built
-  // while they travel.
-  float4 keep[kParkRegs > 0 ? kParkRegs : 1];
-  {
-#pragma unroll
-    for (int k = 0; k < kParkSmem; ++k) {
-      const int c = k * kFusedThreads + tid;
-      float4* dst = park + c;
-      if (4 * c + 3 < len) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(row + 4 * c)
-                     : "memory");
-      } else {
-        *dst = load_chunk(c);  // the ragged last chunk and everything beyond the end (zeros)
+  for (int k = 0; k < kSU; ++k) {
+    const int p = tile0 + 4 * (k * kSThreads + tid);
+    if (!(hit[k] & 1u)) m = max(m, abs_bits(v[k].x));
+    if (!(hit[k] & 2u)) m = max(m, abs_bits(v[k].y));
+    if (!(hit[k] & 4u)) m = max(m, abs_bits(v[k].z));
+    if (!(hit[k] & 8u)) m = max(m, abs_bits(v[k].w));
+    if (copy) {
+      if (p + 3 < len) {
+        *reinterpret_cast<float4*>(ro + p) = v[k];
+      } else if (p < len) {
+        ro[p] = v[k].x;
+        if (p + 1 < len) ro[p + 1] = v[k].y;
+        if (p + 2 < len) ro[p + 2] = v[k].z;
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < kParkRegs; ++k) keep[k] = load_chunk((kParkSmem + k) * kFusedThreads + tid);
-    if (with_isd) {
-      const int nwords = (len + 31) >> 5;
-      for (int w = tid; w < nwords; w += kFusedThreads) smask[w] = 0u;
-      __syncthreads();
-      for (int i0 = ibeg + tid; i0 < iend; i0 += kImpU * kFusedThreads) {  // kImpU positions in flight per thread
-        int p[kImpU];
-#pragma unroll
-        for (int k = 0; k < kImpU; ++k) {
-          const int i = i0 + k * kFusedThreads;
-          p[k] = (i < iend) ? __ldg(isd_idx + i) : -1;
-        }
-#pragma unroll
-        for (int k = 0; k < kImpU; ++k)
-          if (p[k] >= 0 && p[k] < len) atomicOr(smask + (p[k] >> 5), 1u << (p[k] & 31));
-      }
-    }
-    if (with_isd) __syncthreads();  // mask complete
   }
-  // peaks over all samples and over those no impulse touches (zero padding is neutral; NaN propagates like numpy's amax)
-  float m_all = 0.f, m_unt = 0.f;
-  bool nan_all = false, nan_unt = false;
-  auto peak_chunk = [&](const float4& v, int c) {
-    const int p = 4 * c;
-    const uint32_t hit = (with_isd && p < len) ? ((smask[p >> 5] >> (p & 31)) & 0xFu) : 0u;
-    const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float a = fabsf(e[q]);
-      nan_all |= (a != a);
-      m_all = fmaxf(m_all, a);
-      if (!((hit >> q) & 1u)) {
-        nan_unt |= (a != a);
-        m_unt = fmaxf(m_unt, a);
-      }
-    }
-  };
-  // the chunks that do not fit on chip first: their round trips overlap the cp.async traffic of the parked ones
-  for (int c0 = kParkChunks + tid; c0 < nchunk; c0 += kOverU * kFusedThreads) {  // chunks that do not fit on chip
-    float4 v[kOverU];
-#pragma unroll
-    for (int k = 0; k < kOverU; ++k) v[k] = load_chunk(c0 + k * kFusedThreads);
-#pragma unroll
-    for (int k = 0; k < kOverU; ++k) peak_chunk(v[k], c0 + k * kFusedThreads);
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < kParkSmem; ++k) peak_chunk(park[k * kFusedThreads + tid], k * kFusedThreads + tid);
-#pragma unroll
-  for (int k = 0; k < kParkRegs; ++k) peak_chunk(keep[k], (kParkSmem + k) * kFusedThreads + tid);
-  if (nan_all) m_all = NAN;
-  if (nan_unt) m_unt = NAN;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m_all = nan_max(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
-    m_unt = nan_max(m_unt, __shfl_xor_sync(0xffffffffu, m_unt, o));
-  }
-  if (lane == 0) {
-    red[warp][0] = m_all;
-    red[warp][1] = m_unt;
-  }
+  m = block_umax(m, scratch);
+  const int nact = (len + kSTile - 1) / kSTile;  // tiles of this utterance that do work
+  if (tid == 0) s.tile_peak[(size_t)u * s.ntiles + tile] = m;
+  __threadfence();
   __syncthreads();
   if (tid == 0) {
-    float a = red[0][0], b = red[0][1];
-    for (int w = 1; w < kFusedThreads / 32; ++w) {
-      a = nan_max(a, red[w][0]);
-      b = nan_max(b, red[w][1]);
-    }
-    const float div1 = (always || a > 1.f) ? a : 1.f;  // a NaN peak: "NaN > 1" is false, like the reference
-    bc[0] = div1;
-    bc[1] = b / div1;  // peak of the untouched samples after the first normalisation
+    const unsigned prev = atomicAdd(s.counters + u, 1u);
+    s_last = (prev == (unsigned)(nact - 1));
+    if (s_last) s.counters[u] = 0u;  // ready for the next launch
   }
   __syncthreads();
-  const float div1 = bc[0];
-  float div2 = 1.f;
-  if (with_isd) {
-    // the impulses, gathered once: parked samples come from shared memory, the value is stashed for the scatter below
-    __syncthreads();  // the parked chunks of other threads
-    const float* parked = reinterpret_cast<const float*>(park);
-    float mt = 0.f;
-    for (int i0 = ibeg + tid; i0 < iend; i0 += kImpU * kFusedThreads) {  // loads of kImpU impulses issued before their use
-      int p[kImpU];
-      double fr[kImpU];
-      float xv[kImpU];
+  if (!s_last) return;
+  __threadfence();
+
+  // ---- the utterance is complete in `out`: impulses, peak, conditional rescale (all through L2) -----------------------------
+  uint32_t pk = 0u;
+  for (int t = tid; t < nact; t += kSThreads) pk = max(pk, __ldcg(s.tile_peak + (size_t)u * s.ntiles + t));
+  if (kIsd) {
+    const int ibeg = s.isd_off[u], iend = s.isd_off[u + 1];
+    constexpr int kU = 4;  // impulses in flight per thread
+    for (int i0 = ibeg + tid; i0 < iend; i0 += kU * kSThreads) {
+      int p[kU];
+      double fr[kU];
+      float xv[kU];
 #pragma unroll
-      for (int k = 0; k < kImpU; ++k) {
-        const int i = i0 + k * kFusedThreads;
-        p[k] = (i < iend) ? __ldg(isd_idx + i) : -1;
+      for (int k = 0; k < kU; ++k) {
+        const int i = i0 + k * kSThreads;
+        p[k] = (i < iend) ? __ldg(s.isd_idx + i) : -1;
         if (p[k] >= len) p[k] = -1;
       }
 #pragma unroll
-      for (int k = 0; k < kImpU; ++k) {
-        fr[k] = (p[k] >= 0) ? __ldg(isd_fr + i0 + k * kFusedThreads) : 0.0;
-        xv[k] = (p[k] < 0) ? 0.f : (p[k] < kParkSmem * kFusedThreads * 4) ? parked[p[k]] : __ldg(row + p[k]);
+      for (int k = 0; k < kU; ++k) {
+        fr[k] = (p[k] >= 0) ? __ldg(s.isd_fr + i0 + k * kSThreads) : 0.0;
+        xv[k] = (p[k] >= 0) ? __ldcg(ra + p[k]) : 0.f;
       }
 #pragma unroll
-      for (int k = 0; k < kImpU; ++k) {
+      for (int k = 0; k < kU; ++k) {
         if (p[k] >= 0) {
-          const int i = i0 + k * kFusedThreads;
-          const float t = isd_value(__fdiv_rn(xv[k], div1), g_sd, fr[k]);
-          mt = fmaxf(mt, fabsf(t));
-          if (i - ibeg < kStash) stash[i - ibeg] = t;
+          const float t = isd_value(xv[k], s.g_sd, fr[k]);
+          pk = max(pk, abs_bits(t));
+          __stcg(ro + p[k], t);
         }
       }
     }
-    mt = warp_max(mt);
-    __syncthreads();
-    if (lane == 0) red[warp][0] = mt;
-    __syncthreads();
-    if (tid == 0) {
-      float m2 = bc[1];
-      for (int w = 0; w < kFusedThreads / 32; ++w) m2 = fmaxf(m2, red[w][0]);
-      bc[2] = (m2 > 1.f) ? m2 : 1.f;
-    }
-    __syncthreads();
-    div2 = bc[2];
   }
-  // out = (x / div1) / div2 (division by 1 skipped: identity), then the impulses
-  const int ndiv = (div1 != 1.f) + (div2 != 1.f);
-  const float dv = (div1 != 1.f) ? div1 : div2;
-  auto nrm = [&](float e) {
-    if (ndiv == 0) return e;
-    if (ndiv == 1) return __fdiv_rn(e, dv);
-    return __fdiv_rn(__fdiv_rn(e, div1), div2);
-  };
-  auto store_chunk = [&](const float4& v, int c) {
-    const int p = 4 * c;
-    const float4 r = make_float4(nrm(v.x), nrm(v.y), nrm(v.z), nrm(v.w));
-    if (p + 3 < len) {
-      *reinterpret_cast<float4*>(orow + p) = r;
-    } else if (p < len) {
-      orow[p] = r.x;
-      if (p + 1 < len) orow[p + 1] = r.y;
-      if (p + 2 < len) orow[p + 2] = r.z;
-    }
-  };
-  if (nchunk > kParkChunks) {  // the overflow first, from its end: that is what pass 1 left most recently in L2
-    const int span = kOverU * kFusedThreads;
-    const int nsweep = (nchunk - kParkChunks + span - 1) / span;
-    for (int sw = nsweep - 1; sw >= 0; --sw) {
-      const int c0 = kParkChunks + sw * span + tid;
-      float4 v[kOverU];
+  pk = block_umax(pk, scratch);  // (its barriers also order the impulse stores before the rescale below)
+  const float peak = __uint_as_float(pk);
+  if (!(s.always || peak > 1.f)) return;  // a NaN peak: "NaN > 1" is false, like the reference
+  const int nchunk = (len + 3) >> 2;
+  constexpr int kRU = 4;  // chunks in flight per thread: the reads come from L2
+  for (int c0 = tid; c0 < nchunk; c0 += kRU * kSThreads) {
+    float4 w[kRU];
 #pragma unroll
-      for (int k = 0; k < kOverU; ++k) v[k] = load_chunk(c0 + k * kFusedThreads);
-#pragma unroll
-      for (int k = 0; k < kOverU; ++k) store_chunk(v[k], c0 + k * kFusedThreads);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < kParkRegs; ++k) store_chunk(keep[k], (kParkSmem + k) * kFusedThreads + tid);
-#pragma unroll
-  for (int k = 0; k < kParkSmem; ++k) store_chunk(park[k * kFusedThreads + tid], k * kFusedThreads + tid);
-  if (with_isd) {
-    __syncthreads();  // impulse positions overwrite what the dense pass just stored (merged in L2 before reaching HBM)
-    for (int i0 = ibeg + tid; i0 < iend; i0 += kImpU * kFusedThreads) {
-      int p[kImpU];
-#pragma unroll
-      for (int k = 0; k < kImpU; ++k) {
-        const int i = i0 + k * kFusedThreads;
-        p[k] = (i < iend) ? __ldg(isd_idx + i) : -1;
+    for (int k = 0; k < kRU; ++k) {
+      const int p = 4 * (c0 + k * kSThreads);
+      w[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p + 3 < len) {
+        w[k] = __ldcg(reinterpret_cast<const float4*>(ro + p));
+      } else if (p < len) {
+        w[k].x = __ldcg(ro + p);
+        if (p + 1 < len) w[k].y = __ldcg(ro + p + 1);
+        if (p + 2 < len) w[k].z = __ldcg(ro + p + 2);
       }
+    }
 #pragma unroll
-      for (int k = 0; k < kImpU; ++k) {
-        const int i = i0 + k * kFusedThreads;
-        if (p[k] >= 0 && p[k] < len) {
-          const float t = (i - ibeg < kStash) ? stash[i - ibeg] : isd_value(__fdiv_rn(__ldg(row + p[k]), div1), g_sd, isd_fr[i]);
-          orow[p[k]] = __fdiv_rn(t, div2);
-        }
+    for (int k = 0; k < kRU; ++k) {
+      const int p = 4 * (c0 + k * kSThreads);
+      const float4 r = make_float4(__fdiv_rn(w[k].x, peak), __fdiv_rn(w[k].y, peak), __fdiv_rn(w[k].z, peak), __fdiv_rn(w[k].w, peak));
+      if (p + 3 < len) {
+        *reinterpret_cast<float4*>(ro + p) = r;
+      } else if (p < len) {
+        ro[p] = r.x;
+        if (p + 1 < len) ro[p + 1] = r.y;
+        if (p + 2 < len) ro[p + 2] = r.z;
       }
     }
   }
@@ -466,98 +248,59 @@ isd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_ar
 
 }  // namespace
 
+int stream_tiles_for(int ld) { return (ld + kSTile - 1) / kSTile; }
+
 int launch_mask_build(const int32_t* isd_off, const int32_t* isd_idx, const int32_t* len, int B, uint32_t* mask,
                       int mask_ld, cudaStream_t st) {
   if (B <= 0) return RB_OK;
+  if (mask_ld <= kMaskSmemWords) {
+    mask_build_kernel<<<B, kMaskThreads, (size_t)mask_ld * sizeof(uint32_t), st>>>(isd_off, isd_idx, len, mask, mask_ld);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+  }
   RB_CUDA(cudaMemsetAsync(mask, 0, (size_t)B * mask_ld * sizeof(uint32_t), st));
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = min(65535, B - b0);
-    mask_build_kernel<<<dim3(kSparseChunks, nb), 256, 0, st>>>(isd_off + b0, isd_idx, len + b0, mask + (size_t)b0 * mask_ld, mask_ld);
+    mask_build_global_kernel<<<dim3(8, nb), 256, 0, st>>>(isd_off + b0, isd_idx, len + b0, mask + (size_t)b0 * mask_ld, mask_ld);
     RB_LAUNCH_CHECK();
   }
   return RB_OK;
 }
 
-int launch_dense_stats(const float* x, const int32_t* len, int B, int ld, float* stats, const uint32_t* mask, int mask_ld,
-                       cudaStream_t st) {
-  if (B <= 0) return RB_OK;
-  const int ntiles = tiles_for(ld);
-  for (int b0 = 0; b0 < B; b0 += 65535) {
-    const int nb = min(65535, B - b0);
-    dense_stats_kernel<<<dim3(ntiles, nb), kThreads, 0, st>>>(x + (size_t)b0 * ld, len + b0, ld, stats + (size_t)b0 * ntiles * kStatN,
-                                                            mask ? mask + (size_t)b0 * mask_ld : nullptr, mask_ld);
+int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B, int ld, int always, const uint32_t* mask,
+                       int mask_ld, const int32_t* isd_off, const int32_t* isd_idx, const double* isd_fr, float g_sd, float* out,
+                       uint32_t* tile_peak, uint32_t* counters, cudaStream_t st) {
+  if (B <= 0 || ld <= 0) return RB_OK;
+  const bool isd = isd_off != nullptr;
+  if (isd && (!mask || !isd_idx || !isd_fr || b)) return RB_ERR_INVALID_ARG;  // impulses apply to a single input
+  if (!a || !len || !out || !tile_peak || !counters) return RB_ERR_INVALID_ARG;
+  RB_CUDA(cudaMemsetAsync(counters, 0, (size_t)B * sizeof(uint32_t), st));
+  StreamArgs s;
+  s.ld = ld;
+  s.ntiles = stream_tiles_for(ld);
+  s.always = always;
+  s.mask_ld = mask_ld;
+  s.isd_idx = isd_idx;
+  s.isd_fr = isd_fr;
+  s.g_sd = g_sd;
+  const int per = max(1, (int)(0x7fffffff / (long long)s.ntiles));  // utterances per launch (grid.x < 2^31)
+  for (int b0 = 0; b0 < B; b0 += per) {
+    const int nb = min(per, B - b0);
+    s.a = a + (size_t)b0 * ld;
+    s.b = b ? b + (size_t)b0 * ld : nullptr;
+    s.len = len + b0;
+    s.mask = mask ? mask + (size_t)b0 * mask_ld : nullptr;
+    s.isd_off = isd ? isd_off + b0 : nullptr;
+    s.out = out + (size_t)b0 * ld;
+    s.tile_peak = tile_peak + (size_t)b0 * s.ntiles;
+    s.counters = counters + b0;
+    const unsigned grid = (unsigned)nb * (unsigned)s.ntiles;
+    if (isd) norm_stream_kernel<true, false><<<grid, kSThreads, 0, st>>>(s);
+    else if (b) norm_stream_kernel<false, true><<<grid, kSThreads, 0, st>>>(s);
+    else norm_stream_kernel<false, false><<<grid, kSThreads, 0, st>>>(s);
     RB_LAUNCH_CHECK();
   }
   return RB_OK;
 }
 
-int launch_finalize(const FinalizeArgs& args, int B, cudaStream_t st) {
-  if (B <= 0) return RB_OK;
-  finalize_kernel<<<B, kThreads, 0, st>>>(args);
-  RB_LAUNCH_CHECK();
-  return RB_OK;
-}
-
-int launch_ssi_finalize(const float* stats_x, const float* stats_n, int ntiles, const float* snr_db, UttParams* out, int B,
-                        cudaStream_t st) {
-  if (B <= 0) return RB_OK;
-  ssi_finalize_kernel<<<B, 32, 0, st>>>(stats_x, stats_n, ntiles, snr_db, out);
-  RB_LAUNCH_CHECK();
-  return RB_OK;
-}
-
-template <int MODE>
-static int launch_apply_mode(const float* a, const float* b, const int32_t* len, int B, int ld, const UttParams* params,
-                             float* out, cudaStream_t st) {
-  if (B <= 0) return RB_OK;
-  const int ntiles = tiles_for(ld);
-  for (int b0 = 0; b0 < B; b0 += 65535) {
-    const int nb = min(65535, B - b0);
-    apply_kernel<MODE><<<dim3(ntiles, nb), kThreads, 0, st>>>(a + (size_t)b0 * ld, b ? b + (size_t)b0 * ld : nullptr, len + b0, ld,
-                                                            params ? params + b0 : nullptr, out + (size_t)b0 * ld);
-    RB_LAUNCH_CHECK();
-  }
-  return RB_OK;
-}
-
-int launch_apply_affine(const float* in, const int32_t* len, int B, int ld, const UttParams* params, float* out, cudaStream_t st) {
-  return launch_apply_mode<APPLY_AFFINE>(in, nullptr, len, B, ld, params, out, st);
-}
-int launch_apply_ssi(const float* x, const float* noise, const int32_t* len, int B, int ld, const UttParams* params, float* out,
-                     cudaStream_t st) {
-  return launch_apply_mode<APPLY_SSI>(x, noise, len, B, ld, params, out, st);
-}
-int launch_apply_sum(const float* a, const float* b, const int32_t* len, int B, int ld, float* out, cudaStream_t st) {
-  return launch_apply_mode<APPLY_SUM>(a, b, len, B, ld, nullptr, out, st);
-}
-
-int launch_isd_scatter(const float* raw, const int32_t* len, int B, int ld, const int32_t* isd_off, const int32_t* isd_idx,
-                       const double* isd_fr, float g_sd, const UttParams* params, float* out, cudaStream_t st) {
-  if (B <= 0) return RB_OK;
-  for (int b0 = 0; b0 < B; b0 += 65535) {
-    const int nb = min(65535, B - b0);
-    isd_scatter_kernel<<<dim3(kSparseChunks, nb), 256, 0, st>>>(raw + (size_t)b0 * ld, len + b0, ld, isd_off + b0, isd_idx, isd_fr, g_sd,
-                                                                params + b0, out + (size_t)b0 * ld);
-    RB_LAUNCH_CHECK();
-  }
-  return RB_OK;
-}
-
-}  // namespace rb
-
-namespace rb {
-// normWav(x, always) [+ ISD] in one kernel. Returns RB_ERR_UNSUPPORTED when the impulse mask does not fit shared memory
-// (utterances beyond ~1.8 M samples); the caller then takes the multi-pass path.
-int launch_isd_fused(const float* x, const int32_t* len, int B, int ld, int always, const int32_t* isd_off, const int32_t* isd_idx,
-                     const double* isd_fr, float g_sd, float* out, cudaStream_t st) {
-  if (B <= 0) return RB_OK;
-  const size_t smem = (size_t)kParkSmem * kFusedThreads * 16 + (isd_off ? kStash * 4 + ((size_t)(ld + 31) / 32) * 4 : 0);
-  if (smem > (227 / RB_ISD_MIN_BLOCKS) * 1024) return RB_ERR_UNSUPPORTED;  // keeps two CTAs per SM; longer rows take the multi-pass path
-  RB_CUDA(cudaFuncSetAttribute(isd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // without this the driver may pick a carve-out that holds a single CTA per SM
-  RB_CUDA(cudaFuncSetAttribute(isd_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  isd_fused_kernel<<<B, kFusedThreads, smem, st>>>(x, len, ld, always, isd_off, isd_idx, isd_fr, g_sd, out);
-  RB_LAUNCH_CHECK();
-  return RB_OK;
-}
 }  // namespace rb

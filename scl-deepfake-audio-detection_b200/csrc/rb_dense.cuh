@@ -4,37 +4,19 @@
 
 namespace rb {
 
-struct FinalizeArgs {
-  const float* stats;        // [B][ntiles][kStatN]
-  int ntiles;
-  const int32_t* len;        // [B]
-  int center;                // subtract the mean (LnL tail, RawBoost.py:67)
-  int always;                // normWav(x, 1)
-  // impulsive noise applied after the first normalisation (NULL isd_off = none)
-  const float* raw;          // the waveform the statistics were taken from, [B][ld]
-  int ld;
-  const int32_t* isd_off;
-  const int32_t* isd_idx;
-  const double* isd_fr;
-  float g_sd;
-  UttParams* out;            // [B]
-};
-
+// bit p of row u (stride mask_ld words) = 1 iff p is an impulse position of utterance u; every word of the row is written
 int launch_mask_build(const int32_t* isd_off, const int32_t* isd_idx, const int32_t* len, int B, uint32_t* mask,
                       int mask_ld, cudaStream_t st);
-int launch_dense_stats(const float* x, const int32_t* len, int B, int ld, float* stats, const uint32_t* mask, int mask_ld,
-                       cudaStream_t st);
-int launch_finalize(const FinalizeArgs& args, int B, cudaStream_t st);
-int launch_ssi_finalize(const float* stats_x, const float* stats_n, int ntiles, const float* snr_db, UttParams* out, int B,
-                        cudaStream_t st);
-int launch_apply_affine(const float* in, const int32_t* len, int B, int ld, const UttParams* params, float* out, cudaStream_t st);
-int launch_apply_ssi(const float* x, const float* noise, const int32_t* len, int B, int ld, const UttParams* params, float* out,
-                     cudaStream_t st);
-int launch_apply_sum(const float* a, const float* b, const int32_t* len, int B, int ld, float* out, cudaStream_t st);
-int launch_isd_scatter(const float* raw, const int32_t* len, int B, int ld, const int32_t* isd_off, const int32_t* isd_idx,
-                       const double* isd_fr, float g_sd, const UttParams* params, float* out, cudaStream_t st);
 
-int launch_isd_fused(const float* x, const int32_t* len, int B, int ld, int always, const int32_t* isd_off, const int32_t* isd_idx,
-                     const double* isd_fr, float g_sd, float* out, cudaStream_t st);
+// tiles per row of the streaming pass (sizes tile_peak)
+int stream_tiles_for(int ld);
+
+// out = normWav(v, always) where v = a (+ b when b != NULL), or -- with isd_off != NULL (b must be NULL) --
+// out = normWav(a with the impulses applied, always). One streaming launch; see rb_dense.cu.
+// tile_peak: [B][stream_tiles_for(ld)] words, counters: [B] words (zeroed here).
+// out may equal a when b == NULL (in place: the copy is skipped).
+int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B, int ld, int always, const uint32_t* mask,
+                       int mask_ld, const int32_t* isd_off, const int32_t* isd_idx, const double* isd_fr, float g_sd, float* out,
+                       uint32_t* tile_peak, uint32_t* counters, cudaStream_t st);
 
 }  // namespace rb

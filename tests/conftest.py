@@ -36,3 +36,18 @@ def stream_digest():
         "has_gauss": int(has_gauss),
         "cached_gaussian": float(cached),
     }
+
+
+@pytest.fixture(scope="session")
+def golden2():
+    """Round-2 fixtures (oracle/make_golden.py --round2): inputs above full scale, float64 / zero / NaN inputs, utterances
+    longer than 65536 samples, the reverb augmentor and whole Dataset items -- all from the unmodified reference."""
+    arrays = np.load(os.path.join(GOLDEN_DIR, "round2_golden.npz"))
+    with open(os.path.join(GOLDEN_DIR, "round2_golden.json")) as f:
+        meta = json.load(f)
+    return arrays, meta
+
+
+def sha1_of(a):
+    import hashlib
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()

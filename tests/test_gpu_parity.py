@@ -289,3 +289,111 @@ def test_dropin_patches_loader_namespace(eng):
     np.random.seed(5)
     want = orc.process(x, 16000, ARGS, 5)
     assert max_err(y, want) <= TOL and fake.LnL_convolutive_noise is rb.LnL_convolutive_noise
+
+
+# ---------------------------------------------------------------------------------------------------------
+# round-2 fixtures from the unmodified reference: inputs above full scale, float64 / zero / NaN inputs, long utterances
+# ---------------------------------------------------------------------------------------------------------
+def test_inputs_above_full_scale_match_reference(eng, golden2):
+    """Stand-alone ISD must apply its impulses to the RAW x and normalise afterwards (RawBoost.py:76-84): with max|x| > 1 a
+    first normalisation of the input changes which sample carries the peak. Algos 2, 7, 8 and the operator itself."""
+    from conftest import sha1_of, stream_digest
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    arrays, meta = golden2
+    for key, s in meta["over"].items():
+        algo, u = int(key.split("_")[1][4:]), int(key.split("_")[2][1:])
+        x = orc.overscale_utterance(u, 16000)
+        np.random.seed(orc.seed_for(50 + u))
+        y = rb.process_Rawboost_feature(x, 16000, ARGS, algo)
+        assert stream_digest() == s["stream"], key
+        assert max_err(y[np.array(s["probe_idx"])], s["probe_val"]) <= TOL, key
+        assert abs(float(y.astype(np.float64).max()) - s["max"]) <= TOL and abs(float(y.astype(np.float64).min()) - s["min"]) <= TOL, key
+        if algo == 2:
+            assert sha1_of(y) == s["sha1_f32"], "ISD must be bit-exact on float32 input, also above full scale"
+        if key in arrays.files:
+            assert max_err(y, arrays[key]) <= TOL, key
+    for u in (0, 1):
+        np.random.seed(orc.seed_for(50 + u))
+        assert np.array_equal(rb.ISD_additive_noise(orc.overscale_utterance(u, 16000), 10, 2), arrays[f"over_op_isd_u{u}"])
+
+
+def test_float64_zero_and_nan_inputs_match_reference(eng, golden2):
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    arrays, meta = golden2
+    x64 = 0.3 * np.random.RandomState(31).standard_normal(4000)
+    for algo in (1, 2, 3, 5):  # float64 in: the reference computes in float64; here the input is rounded to float32 first
+        np.random.seed(orc.seed_for(60))
+        y = rb.process_Rawboost_feature(x64, 16000, ARGS, algo)
+        assert y.dtype == np.float32 and max_err(y, arrays[f"f64_algo{algo}"]) <= TOL, algo
+    z = np.zeros(1000, dtype=np.float32)
+    xn = orc.synth_utterance(9, 3000, True).copy()
+    xn[100] = np.nan
+    for algo in (1, 2, 3, 5):
+        np.random.seed(orc.seed_for(61))
+        assert np.array_equal(rb.process_Rawboost_feature(z, 16000, ARGS, algo), arrays[f"zeros_algo{algo}"], equal_nan=True), algo
+        np.random.seed(orc.seed_for(62))
+        y = rb.process_Rawboost_feature(xn, 16000, ARGS, algo)
+        ref = arrays[f"nan_algo{algo}"]
+        assert np.array_equal(np.isnan(y), np.isnan(ref)), f"algo {algo}: NaN must propagate exactly like numpy"
+        assert np.allclose(y, ref, rtol=0, atol=TOL, equal_nan=True)
+    assert np.array_equal(rb.normWav(z, 0), z) and np.isnan(rb.normWav(z, 1)).all()  # 0/0 stays NaN, as in the reference
+    assert np.array_equal(rb.normWav(xn, 0), arrays["nan_norm0"], equal_nan=True)
+    assert np.isnan(rb.normWav(xn, 1)).all() and np.isnan(arrays["nan_norm1"]).all()
+
+
+@pytest.mark.parametrize("L", [65537, 100000, 211000])
+def test_long_utterances_match_reference(eng, P, golden2, L):
+    """Un-cropped utterances, as the loaders feed them (asvspoof_2019_augall_3.py:105-117): ISD / normWav bit-exact by digest,
+    algo 5 within tolerance of the reference's summary and of the oracle."""
+    from conftest import sha1_of
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    _, meta = golden2
+    for loud in (0, 1):
+        x = orc.synth_utterance(70 + loud, L, bool(loud))
+        if loud:
+            x = (x * 2.0).astype(np.float32)
+        for algo in (2, 5):
+            s = meta["long"][f"long_algo{algo}_L{L}_loud{loud}"]
+            got, _ = run_batch(eng, P, algo, [x], [orc.seed_for(70)])
+            y = got[0]
+            if algo == 2:
+                assert sha1_of(y) == s["sha1_f32"], (L, loud)
+            else:
+                assert max_err(y[np.array(s["probe_idx"])], s["probe_val"]) <= TOL
+                assert abs(float(np.abs(y.astype(np.float64)).max()) - max(abs(s["min"]), abs(s["max"]))) <= TOL
+                np.random.seed(orc.seed_for(70))
+                assert max_err(y, orc.process(x, 16000, ARGS, 5)) <= TOL
+        for always in (0, 1):
+            assert sha1_of(rb.normWav(x, always)) == meta["long"][f"long_norm{always}_L{L}_loud{loud}"]["sha1_f32"]
+
+
+def test_ragged_batch_with_long_rows(eng, P):
+    """One batch mixing lengths on both sides of 65536 and of the streaming tile (4096): algos 2, 5 and 8 vs the oracle."""
+    lens = [211000, 70001, 65537, 65536, 4097, 4096, 4095, 5, 1]
+    waves = [orc.synth_utterance(20 + i, n, bool(i % 2)) * (2.0 if i % 3 == 0 else 1.0) for i, n in enumerate(lens)]
+    waves = [w.astype(np.float32) for w in waves]
+    seeds = [orc.seed_for(300 + i) for i in range(len(lens))]
+    for algo in (2, 5, 8):
+        got, _ = run_batch(eng, P, algo, waves, seeds)
+        want = oracle_batch(algo, waves, seeds)
+        for n, g, w in zip(lens, got, want):
+            if algo == 2:
+                assert np.array_equal(g, w), f"algo 2, L={n}"
+            else:
+                assert max_err(g, w) <= TOL, f"algo {algo}, L={n}: {max_err(g, w):.3e}"
+
+
+def test_normwav_in_place_and_batched(eng):
+    """rb_normwav with y == x (the copy is skipped) equals the out-of-place result, rows on both sides of the threshold."""
+    rs = np.random.RandomState(4)
+    lens = [64600, 64600, 30000, 4096, 7]
+    waves = [(a * rs.uniform(-1, 1, n)).astype(np.float32) for a, n in zip((0.5, 3.0, 1.0001, 0.999, 2.0), lens)]
+    x, ln = eng.pack_waveforms(waves)
+    for always in (False, True):
+        y = eng.normwav(x, ln, always)
+        z = x.clone()
+        eng.normwav(z, ln, always, out=z)
+        torch.cuda.synchronize()
+        assert torch.equal(y, z)
+        for u, w in enumerate(waves):
+            assert np.array_equal(y[u, :lens[u]].cpu().numpy(), orc.norm_wav(w, always)), (always, u)

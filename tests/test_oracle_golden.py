@@ -183,3 +183,108 @@ def test_oracle_multiview_item_matches_reference(mv_golden):
         assert list(out.shape) == m["shape"]
         assert np.max(np.abs(out.astype(np.float64) - arrays[key])) <= 1e-6, (key, item)
         assert stream_digest() == m["stream"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# round-2 fixtures: edge inputs, long utterances, reverb, whole Dataset items
+# ---------------------------------------------------------------------------------------------------------
+def _check_summary(y, s, key):
+    y = np.asarray(y).astype(np.float64)
+    assert abs(y.min() - s["min"]) <= TOL and abs(y.max() - s["max"]) <= TOL, key
+    assert int(np.argmax(np.abs(y))) == s["argmax_abs"], key
+    np.testing.assert_allclose(y[np.array(s["probe_idx"])], s["probe_val"], rtol=0, atol=TOL, err_msg=key)
+
+
+def test_oracle_inputs_above_full_scale(golden2):
+    """ISD applies its impulses to the raw x and normalises afterwards (RawBoost.py:76-84)."""
+    from conftest import sha1_of
+    arrays, meta = golden2
+    for key, s in meta["over"].items():
+        algo, u = int(key.split("_")[1][4:]), int(key.split("_")[2][1:])
+        x = orc.overscale_utterance(u, 16000)
+        assert np.abs(x).max() > 2.0
+        np.random.seed(orc.seed_for(50 + u))
+        y = np.asarray(orc.process(x, 16000, ARGS, algo))
+        _check_summary(y, s, key)
+        assert stream_digest() == s["stream"], key
+        if algo == 2:
+            assert y.dtype == np.float32 and sha1_of(y) == s["sha1_f32"]
+        if key in arrays.files:
+            assert np.max(np.abs(y.astype(np.float64) - arrays[key])) <= 1e-6, key
+    for u in (0, 1):
+        np.random.seed(orc.seed_for(50 + u))
+        assert np.array_equal(orc.isd(orc.overscale_utterance(u, 16000), 10, 2), arrays[f"over_op_isd_u{u}"])
+
+
+def test_oracle_float64_zero_and_nan_inputs(golden2):
+    arrays, meta = golden2
+    x64 = 0.3 * np.random.RandomState(31).standard_normal(4000)
+    for algo in (1, 2, 3, 5):
+        np.random.seed(orc.seed_for(60))
+        y = np.asarray(orc.process(x64, 16000, ARGS, algo))
+        assert str(y.dtype) == meta["f64"][f"f64_algo{algo}"]["dtype"] == "float64"
+        assert np.max(np.abs(y - arrays[f"f64_algo{algo}"])) <= 1e-6
+        assert stream_digest() == meta["f64"][f"f64_algo{algo}"]["stream"]
+    z = np.zeros(1000, dtype=np.float32)
+    xn = orc.synth_utterance(9, 3000, True).copy()
+    xn[100] = np.nan
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for algo in (1, 2, 3, 5):
+            np.random.seed(orc.seed_for(61))
+            y = np.asarray(orc.process(z, 16000, ARGS, algo)).astype(np.float32)
+            assert np.array_equal(y, arrays[f"zeros_algo{algo}"], equal_nan=True)
+            np.random.seed(orc.seed_for(62))
+            y = np.asarray(orc.process(xn, 16000, ARGS, algo)).astype(np.float32)
+            assert int(np.isnan(y).sum()) == meta["nan"][f"nan_algo{algo}"]["nan_count"]
+            assert np.allclose(y, arrays[f"nan_algo{algo}"], rtol=0, atol=1e-6, equal_nan=True)
+        assert np.array_equal(orc.norm_wav(z, 0), arrays["zeros_norm0"]) and np.isnan(arrays["zeros_norm1"]).all()
+        assert np.isnan(orc.norm_wav(z, 1)).all()
+        assert np.array_equal(orc.norm_wav(xn, 0), arrays["nan_norm0"], equal_nan=True)
+        assert np.array_equal(orc.norm_wav(xn, 1), arrays["nan_norm1"], equal_nan=True)
+
+
+@pytest.mark.parametrize("L", [65537, 100000, 211000])
+def test_oracle_long_utterances(golden2, L):
+    """What the loaders really feed RawBoost: the un-cropped utterance (asvspoof_2019_augall_3.py:105-117)."""
+    from conftest import sha1_of
+    _, meta = golden2
+    for loud in (0, 1):
+        x = orc.synth_utterance(70 + loud, L, bool(loud))
+        if loud:
+            x = (x * 2.0).astype(np.float32)
+        for algo in (2, 5):
+            s = meta["long"][f"long_algo{algo}_L{L}_loud{loud}"]
+            np.random.seed(orc.seed_for(70))
+            y = np.asarray(orc.process(x, 16000, ARGS, algo))
+            _check_summary(y, s, (algo, L, loud))
+            assert stream_digest() == s["stream"]
+            if algo == 2:
+                assert sha1_of(y) == s["sha1_f32"]
+        for always in (0, 1):
+            assert sha1_of(orc.norm_wav(x, always)) == meta["long"][f"long_norm{always}_L{L}_loud{loud}"]["sha1_f32"]
+
+
+def test_oracle_reverb_matches_reference(golden2):
+    """audio_augmentor/reverb.py:33-44 (np.convolve in float32 there; the oracle restates it in float64)."""
+    arrays, meta = golden2
+    rir = arrays["reverb_rir"]
+    for tag, data in (("speech", orc.synth_utterance(80, 20000, False)), ("loud", orc.synth_utterance(81, 7001, True))):
+        y = orc.reverb_convolve(data, rir)
+        ref = arrays[f"reverb_{tag}"]
+        assert y.shape == ref.shape == (meta["reverb"][f"reverb_{tag}"]["len"],)
+        assert np.max(np.abs(y - ref)) <= 1e-5 and abs(np.abs(y).max() - 1.0) <= 1e-12
+
+
+def test_oracle_dataset_item_matches_reference(golden2):
+    """The whole ``Dataset_for.__getitem__`` (asvspoof_2019_augall_3.py:103-146): draws, view order, crop, labels."""
+    arrays, meta = golden2
+    g = meta["getitem"]
+    for idx in (0, 3):
+        m = g[f"getitem{idx}"]
+        np.random.seed(m["seed"])
+        utt, data, label = orc.dataset_item(idx, g["ids"], orc.corpus_wave, orc.make_args(), m["vocoders"], m["num_additional_real"],
+                                            m["trim_length"])
+        assert utt == m["utt"] and list(data.shape) == m["shape"]
+        assert np.max(np.abs(data.astype(np.float64) - arrays[f"getitem{idx}_data"])) <= 1e-6
+        assert np.array_equal(label, arrays[f"getitem{idx}_label"])
+        assert stream_digest() == m["stream"]
