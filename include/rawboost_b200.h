@@ -210,6 +210,13 @@ RB_API int rb_process_host_seeded(rb_ctx* ctx, int algo, const rb_args* args, co
  * out[G][V][length] (what the model consumes). out_len (nullable, device int32[G]) receives the samples written per view. */
 RB_API int rb_multiview_assemble(const float* views, const int32_t* len, int G, int V, int ld, const int32_t* start, int length,
                                  int repeat_pad, int layout, float* out, int32_t* out_len, void* stream);
+/* The same with the views read where they already are: view v of group g is row r = view_row[g*V+v] of `views` (r >= 0) or row
+ * -1-r of `views_b` (r < 0) -- e.g. the original waveforms and their RawBoost results, two [R, ld] buffers with one length
+ * array len[R] -- so assembling an item needs no regrouping copy. view_label (nullable, device float[V]) is broadcast to
+ * labels (device float[G][V]): the label vector of Dataset_for.__getitem__ (asvspoof_2019_augall_3.py:143-146). */
+RB_API int rb_multiview_assemble_ex(const float* views, const float* views_b, const int32_t* view_row, const int32_t* len, int G,
+                                    int V, int ld, const int32_t* start, int length, int repeat_pad, int layout, float* out,
+                                    int32_t* out_len, const float* view_label, float* labels, void* stream);
 
 /* Streaming form of rb_process_host_seeded: queues the whole call and returns at once; *ticket identifies it. Up to two calls
  * may be in flight (a third submit first waits for the oldest), so the copies of consecutive batches follow each other
@@ -218,6 +225,26 @@ RB_API int rb_multiview_assemble(const float* views, const int32_t* len, int G, 
 RB_API int rb_submit_host_seeded(rb_ctx* ctx, int algo, const rb_args* args, const float* x, const int32_t* len,
                                  const uint32_t* seeds, int B, int ld, float* y, uint64_t* ticket);
 RB_API int rb_ctx_wait(rb_ctx* ctx, uint64_t ticket);
+
+/* The general streaming form: where the waveforms come from and where the results go are chosen per call.
+ *   x_kind  RB_IO_HOST_F32    x = host float32 [B, ld]                       (what rb_submit_host_seeded takes)
+ *           RB_IO_HOST_PCM16  x = host int16   [B, ld], ld % 8 == 0: 16-bit PCM as a wav file holds it; converted on the device
+ *                             as sample / 32768 -- exactly what librosa / soundfile return for 16-bit audio -- so the
+ *                             host->device traffic is halved
+ *           RB_IO_DEVICE_F32  x = device float32 [B, ld]; len and seeds are then DEVICE arrays too and use_user_stream must be set
+ *   y_kind  RB_IO_HOST_F32    y = host float32 [B, ld]
+ *           RB_IO_DEVICE_F32  y = device float32 [B, ld]: the results stay on the device, where the consumer of the views
+ *                             lives (main.py:57-60); nothing is copied back
+ *   use_user_stream != 0: the call is ordered after the work already queued on user_stream (a cudaStream_t; NULL = the legacy
+ *   default stream), and user_stream waits for the call's completion, so the caller needs no host synchronisation at all.
+ * Chunking, the device planner and its overlap with the kernels are those of rb_submit_host_seeded; rb_ctx_wait(ticket) waits on
+ * the host. Same ownership rule: every buffer stays valid and untouched until the call has completed. */
+#define RB_IO_HOST_F32 0
+#define RB_IO_HOST_PCM16 1
+#define RB_IO_DEVICE_F32 2
+RB_API int rb_submit_seeded_ex(rb_ctx* ctx, int algo, const rb_args* args, const void* x, int x_kind, const int32_t* len,
+                               const uint32_t* seeds, int B, int ld, void* y, int y_kind, void* user_stream, int use_user_stream,
+                               uint64_t* ticket);
 
 /* ---- measurement helpers (bench.py) ---------------------------------------------------------------------
  * rb_probe_fp32: runs a register-resident FFMA2 (packed=1) or FFMA (packed=0) chain on every SM and

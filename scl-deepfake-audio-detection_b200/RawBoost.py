@@ -32,7 +32,7 @@ __all__ = [
     "SSI_additive_noise", "process_Rawboost_feature", "RawBoost12",
 ]
 
-_DEVICE = int(os.environ.get("RAWBOOST_B200_DEVICE", "0"))
+_DEVICE = None  # engine.default_device(): RAWBOOST_B200_DEVICE, shared with multiview / reverb
 # Who issues the draws of the dispatcher: "native" (default) = the library's bit-exact C++ replica of the numpy calls, run
 # on numpy's own global stream state (about 7x faster than numpy + scipy per utterance; integers, impulse gains, noise and the
 # stream state after the call are identical, taps agree to ~1e-15 before the float32 cast); "numpy" = the numpy / scipy calls
@@ -57,7 +57,9 @@ def _native_planner():
     global _native
     if _native is None:
         from .native_planner import NativePlanner
-        _native = NativePlanner(threads=1, pinned=False)
+        planner = NativePlanner(threads=1, pinned=False)
+        planner.self_check()  # once per process: refuse loudly if this numpy's stream is not the one the replica implements
+        _native = planner
     return _native
 
 

@@ -20,7 +20,9 @@ SYMBOLS = (
     "rb_probe_fp32", "rb_launch_count", "rb_profile_enable", "rb_profile_read", "rb_planner_create", "rb_planner_destroy",
     "rb_planner_draw", "rb_devplan_bytes", "rb_devplan_draw", "rb_process_host_seeded",
     "rb_ctx_set_chunk", "rb_ctx_set_plan_mode", "rb_submit_host_seeded", "rb_ctx_wait", "rb_ctx_trace", "rb_ctx_timeline", "rb_multiview_assemble",
+    "rb_multiview_assemble_ex", "rb_submit_seeded_ex",
 )
+RB_IO_HOST_F32, RB_IO_HOST_PCM16, RB_IO_DEVICE_F32 = 0, 1, 2
 
 
 class RawBoostLibraryError(RuntimeError):
@@ -129,6 +131,10 @@ def load() -> C.CDLL:
     lib.rb_planner_draw.argtypes = [vp, C.POINTER(RbArgs), i32, i32, i32, vp, vp, C.POINTER(RbRngState), C.POINTER(RbPlan)]
     lib.rb_multiview_assemble.restype = i32
     lib.rb_multiview_assemble.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]
+    lib.rb_multiview_assemble_ex.restype = i32
+    lib.rb_multiview_assemble_ex.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.rb_submit_seeded_ex.restype = i32
+    lib.rb_submit_seeded_ex.argtypes = [vp, i32, C.POINTER(RbArgs), vp, i32, vp, vp, i32, i32, vp, i32, vp, i32, C.POINTER(C.c_uint64)]
     lib.rb_submit_host_seeded.restype = i32
     lib.rb_submit_host_seeded.argtypes = [vp, i32, C.POINTER(RbArgs), vp, vp, vp, i32, i32, vp, C.POINTER(C.c_uint64)]
     lib.rb_ctx_wait.restype = i32

@@ -132,14 +132,12 @@ int do_lnl(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
                          with_isd ? w.mask : nullptr, w.mask_ld, tail, st);
 }
 
-// ISD on an existing waveform: x -> out. Mask build + ONE streaming launch (impulses, peak and the conditional rescale happen
-// in its per-utterance tail). The input is NOT normalised first: the reference applies the impulses to the raw x
+// ISD on an existing waveform: x -> out. ONE streaming launch (impulses, peak and the conditional rescale happen in its
+// per-utterance finisher CTAs; no impulse mask is needed). The input is NOT normalised first: the reference applies the impulses to the raw x
 // (RawBoost.py:76-84) and only then normWav(y, 0).
 int do_isd(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl, float* out, const Workspace& w, cudaStream_t st) {
   if (!pl || !pl->isd_off || !pl->isd_idx || !pl->isd_fr) return RB_ERR_PLAN;
-  RB_TRY(launch_mask_build(pl->isd_off, pl->isd_idx, len, B, w.mask, w.mask_ld, st));
-  return launch_norm_stream(x, nullptr, len, B, ld, 0, w.mask, w.mask_ld, pl->isd_off, pl->isd_idx, pl->isd_fr, pl->g_sd, out,
-                            (uint32_t*)w.stats_a, w.counters, st);
+  return launch_norm_stream(x, nullptr, len, B, ld, 0, pl->isd_off, pl->isd_idx, pl->isd_fr, pl->g_sd, out, w.stats_a, st);
 }
 
 // SSI: x -> out (out must not alias x: the tail of one utterance reads x while other tiles still compute statistics of it).
@@ -160,8 +158,7 @@ int do_ssi(const float* x, const int32_t* len, int B, int ld, const rb_plan* pl,
 // normWav: x -> out (out may equal x), or with `add`: normWav(x + add) -> out
 int do_normwav(const float* x, const float* add, const int32_t* len, int B, int ld, int always, float* out, const Workspace& w,
                cudaStream_t st) {
-  return launch_norm_stream(x, add, len, B, ld, always, nullptr, 0, nullptr, nullptr, nullptr, 0.f, out, (uint32_t*)w.stats_a,
-                            w.counters, st);
+  return launch_norm_stream(x, add, len, B, ld, always, nullptr, nullptr, nullptr, 0.f, out, w.stats_a, st);
 }
 
 }  // namespace
@@ -311,7 +308,7 @@ struct CallRes {
   char* planmem = nullptr;  // device-drawn plans of the whole batch (rb_process_host_seeded)
   size_t planmem_bytes = 0;
   std::vector<cudaEvent_t> ev_planned;  // one per chunk
-  cudaEvent_t ev_meta = nullptr, ev_body[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr;
+  cudaEvent_t ev_meta = nullptr, ev_body[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr, ev_user = nullptr;
   bool inflight = false;
   uint64_t ticket = 0;
 };
@@ -353,9 +350,24 @@ struct Take {
   }
 };
 
+// Where a call's waveforms come from and where its results go.
+struct IoSpec {
+  const void* x = nullptr;
+  int x_kind = RB_IO_HOST_F32;   // RB_IO_HOST_F32 | RB_IO_HOST_PCM16 | RB_IO_DEVICE_F32 (then len / seeds are device arrays too)
+  void* y = nullptr;
+  int y_kind = RB_IO_HOST_F32;   // RB_IO_HOST_F32 | RB_IO_DEVICE_F32
+  cudaStream_t user = nullptr;   // device-side ordering: the call starts after the work queued on it and (has_user) it waits for the call
+  bool has_user = false;
+};
+
 // Common driver. plan != NULL: host CSR plan, sliced and uploaded per chunk. plan == NULL: seeds/args given, drawn on the device.
-int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, const rb_args* args,
-                 const uint32_t* seeds, float* y, bool async, uint64_t* ticket) {
+int run_pipeline(rb_ctx* c, int algo, const IoSpec& io, const int32_t* len, int B, int ld, const rb_plan* plan, const rb_args* args,
+                 const uint32_t* seeds, bool async, uint64_t* ticket) {
+  const bool x_dev = io.x_kind == RB_IO_DEVICE_F32, x_pcm = io.x_kind == RB_IO_HOST_PCM16, y_dev = io.y_kind == RB_IO_DEVICE_F32;
+  const float* x = (const float*)io.x;
+  float* y = (float*)io.y;
+  if (x_pcm && ld % 8 != 0) return RB_ERR_ALIGNMENT;
+  if ((x_dev || x_pcm || y_dev) && plan != nullptr) return RB_ERR_INVALID_ARG;  // the host-plan form is host float32 in / out only
   RB_CUDA(cudaSetDevice(c->device));
   CallRes& R = c->res[c->calls & 1];
   if (R.inflight) {  // at most two calls in flight: the one that used this resource set must be complete
@@ -394,14 +406,23 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     RB_CUDA(cudaMalloc((void**)&R.meta, meta_need));
     R.meta_bytes = meta_need;
   }
-  int32_t* d_len = (int32_t*)R.meta;
-  uint32_t* d_seeds = (uint32_t*)(R.meta + align_up((size_t)B * 4, 256));
+  const int32_t* d_len = (int32_t*)R.meta;
+  const uint32_t* d_seeds = (uint32_t*)(R.meta + align_up((size_t)B * 4, 256));
   uint64_t h2d = 0, d2h = 0;
-  RB_CUDA(cudaMemcpyAsync(d_len, len, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
-  h2d += (size_t)B * 4;
-  if (devplan) {
-    RB_CUDA(cudaMemcpyAsync(d_seeds, seeds, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
+  if (io.has_user || x_dev) {  // everything of this call comes after what the caller queued on its stream
+    RB_CUDA(cudaEventRecord(R.ev_user, io.user));
+    RB_CUDA(cudaStreamWaitEvent(c->s_in, R.ev_user, 0));
+  }
+  if (x_dev) {  // lengths and seeds are already on the device
+    d_len = len;
+    d_seeds = seeds;
+  } else {
+    RB_CUDA(cudaMemcpyAsync((void*)d_len, len, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
     h2d += (size_t)B * 4;
+    if (devplan) {
+      RB_CUDA(cudaMemcpyAsync((void*)d_seeds, seeds, (size_t)B * 4, cudaMemcpyHostToDevice, c->s_in));
+      h2d += (size_t)B * 4;
+    }
   }
   RB_CUDA(cudaEventRecord(R.ev_meta, c->s_in));
   RB_CUDA(cudaStreamWaitEvent(c->s_plan, R.ev_meta, 0));
@@ -435,7 +456,7 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     }
   }
   Take take;
-  const size_t o_x = take(wave), o_y = take(wave), o_ws = take(ws_bytes);
+  const size_t o_x = take(x_dev ? 0 : wave), o_x16 = take(x_pcm ? wave / 2 : 0), o_y = take(y_dev ? 0 : wave), o_ws = take(ws_bytes);
   const size_t o_lo = take(use_lnl && !devplan ? ((size_t)chunk * n_f + 1) * 4 : 0), o_lt = take(max_lt * 4);
   const size_t o_io = take(use_isd && !devplan ? (size_t)(chunk + 1) * 4 : 0), o_ii = take(max_isd * 4), o_if = take(max_isd * 8);
   const size_t o_sn = take(use_ssi && !devplan ? wave : 0), o_so = take(use_ssi && !devplan ? (size_t)(chunk + 1) * 4 : 0),
@@ -503,8 +524,13 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     const size_t cw = (size_t)bc * ld * sizeof(float);
     // ---- stage 1: host -> device ------------------------------------------------------------------------------------
     if (c->seq + ci >= kSlots) RB_CUDA(cudaStreamWaitEvent(c->s_in, sl.ev_out, 0));  // the slot's previous chunk has left the device
-    RB_CUDA(cudaMemcpyAsync(d + o_x, x + (size_t)u0 * ld, cw, cudaMemcpyHostToDevice, c->s_in));
-    h2d += cw;
+    if (x_pcm) {
+      RB_CUDA(cudaMemcpyAsync(d + o_x16, (const int16_t*)io.x + (size_t)u0 * ld, cw / 2, cudaMemcpyHostToDevice, c->s_in));
+      h2d += cw / 2;
+    } else if (!x_dev) {
+      RB_CUDA(cudaMemcpyAsync(d + o_x, x + (size_t)u0 * ld, cw, cudaMemcpyHostToDevice, c->s_in));
+      h2d += cw;
+    }
     rb_plan dp;
     memset(&dp, 0, sizeof(dp));
     if (active && !devplan) {
@@ -568,19 +594,28 @@ int run_pipeline(rb_ctx* c, int algo, const float* x, const int32_t* len, int B,
     }
     if (!devplan) mark(2, c->s_in);
     RB_CUDA(cudaStreamWaitEvent(c->s_cmp, sl.ev_in, 0));
-    RB_TRY(rb_process(algo, (const float*)(d + o_x), d_len + u0, bc, ld, active ? &dp : nullptr, (float*)(d + o_y), d + o_ws, ws_bytes,
-                      c->s_cmp));
+    if (x_pcm) {
+      RB_TRY(launch_pcm16_to_f32((const int16_t*)(d + o_x16), (float*)(d + o_x), (size_t)bc * ld, c->s_cmp));
+    }
+    const float* xin = x_dev ? x + (size_t)u0 * ld : (const float*)(d + o_x);
+    float* yout = y_dev ? y + (size_t)u0 * ld : (float*)(d + o_y);
+    RB_TRY(rb_process(algo, xin, d_len + u0, bc, ld, active ? &dp : nullptr, yout, d + o_ws, ws_bytes, c->s_cmp));
     RB_CUDA(cudaEventRecord(sl.ev_done, c->s_cmp));
     mark(3, c->s_cmp);
-    // ---- stage 3: device -> host -------------------------------------------------------------------------------------
-    RB_CUDA(cudaStreamWaitEvent(c->s_out, sl.ev_done, 0));
-    RB_CUDA(cudaMemcpyAsync(y + (size_t)u0 * ld, d + o_y, cw, cudaMemcpyDeviceToHost, c->s_out));
-    d2h += cw;
-    RB_CUDA(cudaEventRecord(sl.ev_out, c->s_out));
-    mark(4, c->s_out);
+    // ---- stage 3: device -> host (or nothing: the results stay where the kernels wrote them) ---------------------------
+    if (y_dev) {
+      RB_CUDA(cudaEventRecord(sl.ev_out, c->s_cmp));
+    } else {
+      RB_CUDA(cudaStreamWaitEvent(c->s_out, sl.ev_done, 0));
+      RB_CUDA(cudaMemcpyAsync(y + (size_t)u0 * ld, d + o_y, cw, cudaMemcpyDeviceToHost, c->s_out));
+      d2h += cw;
+      RB_CUDA(cudaEventRecord(sl.ev_out, c->s_out));
+    }
+    mark(4, y_dev ? c->s_cmp : c->s_out);
   }
   c->seq += (uint64_t)nchunks;
-  RB_CUDA(cudaEventRecord(R.ev_done, c->s_out));
+  RB_CUDA(cudaEventRecord(R.ev_done, y_dev ? c->s_cmp : c->s_out));
+  if (io.has_user) RB_CUDA(cudaStreamWaitEvent(io.user, R.ev_done, 0));  // the caller's stream continues after the results exist
   R.inflight = true;
   R.ticket = ++c->calls;
   if (ticket) *ticket = R.ticket;
@@ -644,7 +679,7 @@ int rb_ctx_create(rb_ctx** out, int device) {
   for (cudaStream_t* s : {&c->s_plan, &c->s_apply})
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_lo);
   for (CallRes& R : c->res)
-    for (cudaEvent_t* ev : {&R.ev_meta, &R.ev_body[0], &R.ev_body[1], &R.ev_body[2], &R.ev_done})
+    for (cudaEvent_t* ev : {&R.ev_meta, &R.ev_body[0], &R.ev_body[1], &R.ev_body[2], &R.ev_done, &R.ev_user})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   for (Slot& sl : c->slot)
     for (cudaEvent_t* ev : {&sl.ev_in, &sl.ev_planned, &sl.ev_done, &sl.ev_out})
@@ -670,7 +705,7 @@ int rb_ctx_destroy(rb_ctx* c) {
     if (R.meta) cudaFree(R.meta);
     if (R.planmem) cudaFree(R.planmem);
     for (cudaEvent_t e : R.ev_planned) cudaEventDestroy(e);
-    for (cudaEvent_t e : {R.ev_meta, R.ev_body[0], R.ev_body[1], R.ev_body[2], R.ev_done})
+    for (cudaEvent_t e : {R.ev_meta, R.ev_body[0], R.ev_body[1], R.ev_body[2], R.ev_done, R.ev_user})
       if (e) cudaEventDestroy(e);
   }
   for (cudaStream_t s : {c->s_in, c->s_plan, c->s_apply, c->s_cmp, c->s_out})
@@ -720,11 +755,18 @@ static int check_host_batch(const rb_ctx* c, const float* x, const int32_t* len,
   return RB_OK;
 }
 
+static IoSpec host_io(const float* x, float* y) {
+  IoSpec io;
+  io.x = x;
+  io.y = y;
+  return io;
+}
+
 int rb_process_host(rb_ctx* c, int algo, const float* x, const int32_t* len, int B, int ld, const rb_plan* plan, float* y) {
   RB_TRY(check_host_batch(c, x, len, B, ld, y));
   if (B == 0 || ld == 0) return RB_OK;
   if (algo >= 1 && algo <= 8 && !plan) return RB_ERR_PLAN;
-  return run_pipeline(c, algo, x, len, B, ld, plan, nullptr, nullptr, y, false, nullptr);
+  return run_pipeline(c, algo, host_io(x, y), len, B, ld, plan, nullptr, nullptr, false, nullptr);
 }
 
 int rb_process_host_seeded(rb_ctx* c, int algo, const rb_args* args, const float* x, const int32_t* len, const uint32_t* seeds, int B,
@@ -732,7 +774,7 @@ int rb_process_host_seeded(rb_ctx* c, int algo, const rb_args* args, const float
   RB_TRY(check_host_batch(c, x, len, B, ld, y));
   if (B == 0 || ld == 0) return RB_OK;
   if (algo >= 1 && algo <= 8 && (!args || !seeds)) return RB_ERR_INVALID_ARG;
-  return run_pipeline(c, algo, x, len, B, ld, nullptr, args, seeds, y, false, nullptr);
+  return run_pipeline(c, algo, host_io(x, y), len, B, ld, nullptr, args, seeds, false, nullptr);
 }
 
 int rb_submit_host_seeded(rb_ctx* c, int algo, const rb_args* args, const float* x, const int32_t* len, const uint32_t* seeds, int B,
@@ -741,7 +783,28 @@ int rb_submit_host_seeded(rb_ctx* c, int algo, const rb_args* args, const float*
   RB_TRY(check_host_batch(c, x, len, B, ld, y));
   if (B == 0 || ld == 0) return RB_OK;
   if (algo >= 1 && algo <= 8 && (!args || !seeds)) return RB_ERR_INVALID_ARG;
-  return run_pipeline(c, algo, x, len, B, ld, nullptr, args, seeds, y, true, ticket);
+  return run_pipeline(c, algo, host_io(x, y), len, B, ld, nullptr, args, seeds, true, ticket);
+}
+
+int rb_submit_seeded_ex(rb_ctx* c, int algo, const rb_args* args, const void* x, int x_kind, const int32_t* len, const uint32_t* seeds,
+                        int B, int ld, void* y, int y_kind, void* user_stream, int use_user_stream, uint64_t* ticket) {
+  if (ticket) *ticket = 0;
+  if (x_kind != RB_IO_HOST_F32 && x_kind != RB_IO_HOST_PCM16 && x_kind != RB_IO_DEVICE_F32) return RB_ERR_INVALID_ARG;
+  if (y_kind != RB_IO_HOST_F32 && y_kind != RB_IO_DEVICE_F32) return RB_ERR_INVALID_ARG;
+  RB_TRY(check_host_batch(c, (const float*)x, len, B, ld, (const float*)y));
+  if (B == 0 || ld == 0) return RB_OK;
+  if (algo >= 1 && algo <= 8 && (!args || !seeds)) return RB_ERR_INVALID_ARG;
+  if (x_kind == RB_IO_DEVICE_F32 && !use_user_stream) return RB_ERR_INVALID_ARG;  // device input needs the stream that produced it
+  if ((x_kind == RB_IO_DEVICE_F32 && ((uintptr_t)x & 15u)) || (y_kind == RB_IO_DEVICE_F32 && ((uintptr_t)y & 15u))) return RB_ERR_ALIGNMENT;
+  if (x_kind == RB_IO_DEVICE_F32 && x == y && algo >= 1 && algo <= 8) return RB_ERR_INVALID_ARG;
+  IoSpec io;
+  io.x = x;
+  io.x_kind = x_kind;
+  io.y = y;
+  io.y_kind = y_kind;
+  io.user = (cudaStream_t)user_stream;
+  io.has_user = use_user_stream != 0;
+  return run_pipeline(c, algo, io, len, B, ld, nullptr, args, seeds, true, ticket);
 }
 
 int rb_ctx_wait(rb_ctx* c, uint64_t ticket) {

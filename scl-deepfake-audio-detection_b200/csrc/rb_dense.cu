@@ -67,15 +67,33 @@ mask_build_global_kernel(const int32_t* __restrict__ isd_off, const int32_t* __r
 }
 
 // ---- the streaming pass ---------------------------------------------------------------------------------------------------
+// Grid: per utterance `ntiles` tile CTAs followed by ONE finisher CTA (block index u * (ntiles + 1) + j). Tile CTAs never wait:
+// load, peak, store, release-increment the utterance's arrival counter, exit. The finisher spins (one thread, acquire loads)
+// until all tiles of its utterance have arrived -- they were dispatched before it, so they always make progress -- and then
+// owns the row: impulses, exact peak, conditional rescale, all through L2.
 #ifndef RB_STREAM_THREADS
-#define RB_STREAM_THREADS 256
+#define RB_STREAM_THREADS 512
 #endif
 #ifndef RB_STREAM_CHUNKS
 #define RB_STREAM_CHUNKS 4
 #endif
+#ifndef RB_STREAM_SUBTILES
+#define RB_STREAM_SUBTILES 4
+#endif
+#ifndef RB_STREAM_MIN_BLOCKS
+#define RB_STREAM_MIN_BLOCKS 2
+#endif
+#ifndef RB_STREAM_IMP_U
+#define RB_STREAM_IMP_U 8
+#endif
+#ifndef RB_STREAM_RESCALE_U
+#define RB_STREAM_RESCALE_U 8
+#endif
 constexpr int kSThreads = RB_STREAM_THREADS;     // threads per CTA
-constexpr int kSU = RB_STREAM_CHUNKS;            // float4 chunks per thread, all in flight at once
-constexpr int kSTile = kSThreads * kSU * 4;      // samples per CTA (4096)
+constexpr int kSU = RB_STREAM_CHUNKS;            // float4 chunks per thread and sub-tile
+constexpr int kSub = RB_STREAM_SUBTILES;         // sub-tiles per tile CTA (two of them in flight at any time)
+constexpr int kSTile = kSThreads * kSU * kSub * 4;  // samples per tile CTA (32768)
+constexpr uint32_t kInfBits = 0x7f800000u;
 
 __device__ __forceinline__ uint32_t abs_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
 
@@ -92,6 +110,15 @@ __device__ __forceinline__ uint32_t block_umax(uint32_t v, uint32_t* scratch) {
   return r;
 }
 
+__device__ __forceinline__ void red_release_add(uint32_t* addr, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+
 struct StreamArgs {
   const float* a;            // [B][ld] input
   const float* b;            // [B][ld] second addend (kSum) or nullptr
@@ -99,124 +126,178 @@ struct StreamArgs {
   int ld;
   int ntiles;                // tiles per row = ceil(ld / kSTile)
   int always;                // normWav(., 1)
-  const uint32_t* mask;      // [B][mask_ld] impulse bit mask (kIsd)
-  int mask_ld;
   const int32_t* isd_off;    // kIsd: impulses of utterance u are [off[u], off[u+1])
   const int32_t* isd_idx;
   const double* isd_fr;
   float g_sd;
   float* out;                // [B][ld]; may equal a when !kSum (in place: the copy is skipped)
-  uint32_t* tile_peak;       // [B][ntiles] bit patterns of the per-tile peaks
-  uint32_t* counters;        // [B] arrival counters, zero on entry, left zero
+  uint2* state;              // [B] {peak bits, tiles arrived}; zero on entry, left zero
 };
 
-#ifndef RB_STREAM_MIN_BLOCKS
-#define RB_STREAM_MIN_BLOCKS 6
-#endif
 template <bool kIsd, bool kSum>
 __global__ void __launch_bounds__(kSThreads, RB_STREAM_MIN_BLOCKS)
 norm_stream_kernel(const StreamArgs s) {
   __shared__ uint32_t scratch[kSThreads / 32];
-  __shared__ int s_last;
-  const int u = blockIdx.x / s.ntiles, tile = blockIdx.x - u * s.ntiles;
+  const int per = s.ntiles + 1;
+  const int u = blockIdx.x / per, tile = blockIdx.x - u * per;
   const int tid = threadIdx.x;
-  const int len = s.len[u];
-  const int tile0 = tile * kSTile;
-  if (tile0 >= len) return;
+  const int len = min(s.len[u], s.ld);  // (a length beyond the row stride would leave the finisher waiting for tiles that do not exist)
   const float* ra = s.a + (size_t)u * s.ld;
-  const float* rb_ = kSum ? s.b + (size_t)u * s.ld : nullptr;
   float* ro = s.out + (size_t)u * s.ld;
-  const bool copy = kSum || (ro != ra);
+  uint32_t* st_peak = &s.state[u].x;
+  uint32_t* st_count = &s.state[u].y;
 
-  float4 v[kSU];
-  uint32_t hit[kSU];
+  if (tile < s.ntiles) {
+    // ---- tile CTA: copy + peak ------------------------------------------------------------------------------------------
+    const int tile0 = tile * kSTile;
+    if (tile0 >= len) return;
+    const float* rb_ = kSum ? s.b + (size_t)u * s.ld : nullptr;
+    const bool copy = kSum || (ro != ra);
+    // kSub sub-tiles of kSU chunks per thread, software-pipelined: the loads of sub-tile j+1 are in flight while sub-tile j
+    // is reduced and stored, so the CTA keeps requests outstanding for most of its life instead of only at its start.
+    auto load_sub = [&](int j, float4 (&v)[kSU]) {
 #pragma unroll
-  for (int k = 0; k < kSU; ++k) {  // every load of the tile is issued before the first use
-    const int p = tile0 + 4 * (k * kSThreads + tid);
-    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    hit[k] = 0u;
-    if (p + 3 < len) {
-      v[k] = __ldg(reinterpret_cast<const float4*>(ra + p));
-      if (kSum) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(rb_ + p));
-        v[k] = make_float4(__fadd_rn(v[k].x, w.x), __fadd_rn(v[k].y, w.y), __fadd_rn(v[k].z, w.z), __fadd_rn(v[k].w, w.w));
-      }
-    } else if (p < len) {  // the ragged last chunk; zeros beyond the end are neutral for the peak
-      float e[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int q = 0; q < 4; ++q)
-        if (p + q < len) e[q] = kSum ? __fadd_rn(__ldg(ra + p + q), __ldg(rb_ + p + q)) : __ldg(ra + p + q);
-      v[k] = make_float4(e[0], e[1], e[2], e[3]);
-    }
-    if (kIsd && p < len) hit[k] = (__ldg(s.mask + (size_t)u * s.mask_ld + (p >> 5)) >> (p & 31)) & 0xFu;
-  }
-  uint32_t m = 0u;  // peak of the samples no impulse touches
-#pragma unroll
-  for (int k = 0; k < kSU; ++k) {
-    const int p = tile0 + 4 * (k * kSThreads + tid);
-    if (!(hit[k] & 1u)) m = max(m, abs_bits(v[k].x));
-    if (!(hit[k] & 2u)) m = max(m, abs_bits(v[k].y));
-    if (!(hit[k] & 4u)) m = max(m, abs_bits(v[k].z));
-    if (!(hit[k] & 8u)) m = max(m, abs_bits(v[k].w));
-    if (copy) {
-      if (p + 3 < len) {
-        *reinterpret_cast<float4*>(ro + p) = v[k];
-      } else if (p < len) {
-        ro[p] = v[k].x;
-        if (p + 1 < len) ro[p + 1] = v[k].y;
-        if (p + 2 < len) ro[p + 2] = v[k].z;
-      }
-    }
-  }
-  m = block_umax(m, scratch);
-  const int nact = (len + kSTile - 1) / kSTile;  // tiles of this utterance that do work
-  if (tid == 0) s.tile_peak[(size_t)u * s.ntiles + tile] = m;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned prev = atomicAdd(s.counters + u, 1u);
-    s_last = (prev == (unsigned)(nact - 1));
-    if (s_last) s.counters[u] = 0u;  // ready for the next launch
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-
-  // ---- the utterance is complete in `out`: impulses, peak, conditional rescale (all through L2) -----------------------------
-  uint32_t pk = 0u;
-  for (int t = tid; t < nact; t += kSThreads) pk = max(pk, __ldcg(s.tile_peak + (size_t)u * s.ntiles + t));
-  if (kIsd) {
-    const int ibeg = s.isd_off[u], iend = s.isd_off[u + 1];
-    constexpr int kU = 4;  // impulses in flight per thread
-    for (int i0 = ibeg + tid; i0 < iend; i0 += kU * kSThreads) {
-      int p[kU];
-      double fr[kU];
-      float xv[kU];
-#pragma unroll
-      for (int k = 0; k < kU; ++k) {
-        const int i = i0 + k * kSThreads;
-        p[k] = (i < iend) ? __ldg(s.isd_idx + i) : -1;
-        if (p[k] >= len) p[k] = -1;
-      }
-#pragma unroll
-      for (int k = 0; k < kU; ++k) {
-        fr[k] = (p[k] >= 0) ? __ldg(s.isd_fr + i0 + k * kSThreads) : 0.0;
-        xv[k] = (p[k] >= 0) ? __ldcg(ra + p[k]) : 0.f;
-      }
-#pragma unroll
-      for (int k = 0; k < kU; ++k) {
-        if (p[k] >= 0) {
-          const float t = isd_value(xv[k], s.g_sd, fr[k]);
-          pk = max(pk, abs_bits(t));
-          __stcg(ro + p[k], t);
+      for (int k = 0; k < kSU; ++k) {
+        const int p = tile0 + 4 * ((j * kSU + k) * kSThreads + tid);
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p + 3 < len) {
+          v[k] = __ldg(reinterpret_cast<const float4*>(ra + p));
+          if (kSum) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(rb_ + p));
+            v[k] = make_float4(__fadd_rn(v[k].x, w.x), __fadd_rn(v[k].y, w.y), __fadd_rn(v[k].z, w.z), __fadd_rn(v[k].w, w.w));
+          }
+        } else if (p < len) {  // the ragged last chunk; zeros beyond the end are neutral for the peak
+          float e[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int q = 0; q < 4; ++q)
+            if (p + q < len) e[q] = kSum ? __fadd_rn(__ldg(ra + p + q), __ldg(rb_ + p + q)) : __ldg(ra + p + q);
+          v[k] = make_float4(e[0], e[1], e[2], e[3]);
         }
       }
+    };
+    uint32_t m = 0u;
+    auto consume_sub = [&](int j, const float4 (&v)[kSU]) {
+#pragma unroll
+      for (int k = 0; k < kSU; ++k) {
+        const int p = tile0 + 4 * ((j * kSU + k) * kSThreads + tid);
+        m = max(max(m, abs_bits(v[k].x)), max(abs_bits(v[k].y), max(abs_bits(v[k].z), abs_bits(v[k].w))));
+        if (copy) {
+          if (p + 3 < len) {
+            *reinterpret_cast<float4*>(ro + p) = v[k];
+          } else if (p < len) {
+            ro[p] = v[k].x;
+            if (p + 1 < len) ro[p + 1] = v[k].y;
+            if (p + 2 < len) ro[p + 2] = v[k].z;
+          }
+        }
+      }
+    };
+    float4 va[kSU], vb[kSU];
+    load_sub(0, va);
+#pragma unroll
+    for (int j = 0; j < kSub; j += 2) {
+      if (j + 1 < kSub) load_sub(j + 1, vb);
+      consume_sub(j, va);
+      if (j + 2 < kSub) load_sub(j + 2, va);
+      if (j + 1 < kSub) consume_sub(j + 1, vb);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((tid & 31) == 0) scratch[tid >> 5] = m;
+    __threadfence();  // this thread's stores are visible device-wide before the arrival below
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t r = scratch[0];
+#pragma unroll
+      for (int w = 1; w < kSThreads / 32; ++w) r = max(r, scratch[w]);
+      if (r) atomicMax(st_peak, r);
+      red_release_add(st_count, 1u);  // release: the peak update above is ordered before the arrival
+    }
+    return;
+  }
+
+  // ---- finisher CTA: impulses, exact peak, conditional rescale (all through L2) ---------------------------------------------
+  const int nact = (len + kSTile - 1) / kSTile;  // tiles of this utterance that do work
+  if (nact <= 0) return;
+  // The impulse values depend on the INPUT only, so the first round of them (all of them for a typical utterance) is
+  // gathered and evaluated before the row is complete; only their stores have to wait for the tiles.
+  constexpr int kU = RB_STREAM_IMP_U;  // impulses in flight per thread
+  const int ibeg = kIsd ? s.isd_off[u] : 0, iend = kIsd ? s.isd_off[u + 1] : 0;
+  uint32_t mt = 0u, mx = 0u;  // largest new magnitude / largest magnitude an impulse replaced
+  int p0[kU];
+  float t0[kU];
+  auto impulse_round = [&](int i0, int (&p)[kU], float (&t)[kU]) {
+    double fr[kU];
+    float xv[kU];
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      const int i = i0 + k * kSThreads;
+      p[k] = (i < iend) ? __ldg(s.isd_idx + i) : -1;
+      if (p[k] >= len) p[k] = -1;
+    }
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      fr[k] = (p[k] >= 0) ? __ldg(s.isd_fr + i0 + k * kSThreads) : 0.0;
+      xv[k] = (p[k] >= 0) ? __ldcg(ra + p[k]) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kU; ++k) {
+      t[k] = 0.f;
+      if (p[k] >= 0) {
+        t[k] = isd_value(xv[k], s.g_sd, fr[k]);  // y[p] = x[p] + g_sd * x[p] * f_r  (RawBoost.py:81-82)
+        mx = max(mx, abs_bits(xv[k]));
+        mt = max(mt, abs_bits(t[k]));
+      }
+    }
+  };
+  if (kIsd) impulse_round(ibeg + tid, p0, t0);
+  if (tid == 0) {
+    while (ld_acquire(st_count) < (uint32_t)nact) __nanosleep(40);
+  }
+  __syncthreads();
+  const uint32_t M = __ldcg(st_peak);  // max |v| over the whole row
+  __syncthreads();
+  if (tid == 0) {  // ready for the next launch
+    *st_peak = 0u;
+    *st_count = 0u;
+  }
+  uint32_t pk = M;
+  const int nchunk = (len + 3) >> 2;
+  if (kIsd) {
+#pragma unroll
+    for (int k = 0; k < kU; ++k)
+      if (p0[k] >= 0) __stcg(ro + p0[k], t0[k]);
+    for (int i0 = ibeg + tid + kU * kSThreads; i0 < iend; i0 += kU * kSThreads) {  // utterances with more impulses
+      int p[kU];
+      float t[kU];
+      impulse_round(i0, p, t);
+#pragma unroll
+      for (int k = 0; k < kU; ++k)
+        if (p[k] >= 0) __stcg(ro + p[k], t[k]);
+    }
+    mt = block_umax(mt, scratch);
+    mx = block_umax(mx, scratch);  // (these barriers also order the impulse stores before any read of the row below)
+    // The peak of y = max(peak of the untouched samples, mt). The untouched peak is M unless the row's largest sample was
+    // itself replaced (mx == M); even then nothing more is needed when a new value reaches M, or when nothing can exceed 1.
+    if (mx < M || mt >= M) {
+      pk = max(M, mt);
+    } else if (M <= __float_as_uint(1.f)) {
+      pk = M;  // some value <= M <= 1: no rescale either way
+    } else {   // rare: take the peak of y itself
+      uint32_t r = 0u;
+      for (int c = tid; c < nchunk; c += kSThreads) {
+        const int q = 4 * c;
+        if (q + 3 < len) {
+          const float4 w = __ldcg(reinterpret_cast<const float4*>(ro + q));
+          r = max(max(r, abs_bits(w.x)), max(abs_bits(w.y), max(abs_bits(w.z), abs_bits(w.w))));
+        } else {
+          for (int e = q; e < len; ++e) r = max(r, abs_bits(__ldcg(ro + e)));
+        }
+      }
+      pk = block_umax(r, scratch);
     }
   }
-  pk = block_umax(pk, scratch);  // (its barriers also order the impulse stores before the rescale below)
   const float peak = __uint_as_float(pk);
   if (!(s.always || peak > 1.f)) return;  // a NaN peak: "NaN > 1" is false, like the reference
-  const int nchunk = (len + 3) >> 2;
-  constexpr int kRU = 4;  // chunks in flight per thread: the reads come from L2
+  constexpr int kRU = RB_STREAM_RESCALE_U;  // chunks in flight per thread: the reads come from L2
   for (int c0 = tid; c0 < nchunk; c0 += kRU * kSThreads) {
     float4 w[kRU];
 #pragma unroll
@@ -246,9 +327,35 @@ norm_stream_kernel(const StreamArgs s) {
   }
 }
 
+// 16-bit PCM -> float32, the conversion a wav reader applies (sample / 32768: exact in float32). n8 = groups of 8 samples.
+__global__ void __launch_bounds__(256)
+pcm16_to_f32_kernel(const int4* __restrict__ in, float4* __restrict__ out, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const int4 v = __ldg(in + i);
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f[2 * k] = (float)(short)(w[k] & 0xffff) * (1.f / 32768.f);
+      f[2 * k + 1] = (float)(short)((unsigned)w[k] >> 16) * (1.f / 32768.f);
+    }
+    out[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+    out[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
 }  // namespace
 
 int stream_tiles_for(int ld) { return (ld + kSTile - 1) / kSTile; }
+
+int launch_pcm16_to_f32(const int16_t* in, float* out, size_t n, cudaStream_t st) {
+  if (n == 0) return RB_OK;
+  if (n % 8 != 0 || ((uintptr_t)in & 15u) || ((uintptr_t)out & 15u)) return RB_ERR_ALIGNMENT;
+  const size_t n8 = n / 8;
+  pcm16_to_f32_kernel<<<(unsigned)min((n8 + 255) / 256, (size_t)148 * 16), 256, 0, st>>>((const int4*)in, (float4*)out, n8);
+  RB_LAUNCH_CHECK();
+  return RB_OK;
+}
 
 int launch_mask_build(const int32_t* isd_off, const int32_t* isd_idx, const int32_t* len, int B, uint32_t* mask,
                       int mask_ld, cudaStream_t st) {
@@ -267,34 +374,30 @@ int launch_mask_build(const int32_t* isd_off, const int32_t* isd_idx, const int3
   return RB_OK;
 }
 
-int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B, int ld, int always, const uint32_t* mask,
-                       int mask_ld, const int32_t* isd_off, const int32_t* isd_idx, const double* isd_fr, float g_sd, float* out,
-                       uint32_t* tile_peak, uint32_t* counters, cudaStream_t st) {
+int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B, int ld, int always, const int32_t* isd_off,
+                       const int32_t* isd_idx, const double* isd_fr, float g_sd, float* out, void* state, cudaStream_t st) {
   if (B <= 0 || ld <= 0) return RB_OK;
   const bool isd = isd_off != nullptr;
-  if (isd && (!mask || !isd_idx || !isd_fr || b)) return RB_ERR_INVALID_ARG;  // impulses apply to a single input
-  if (!a || !len || !out || !tile_peak || !counters) return RB_ERR_INVALID_ARG;
-  RB_CUDA(cudaMemsetAsync(counters, 0, (size_t)B * sizeof(uint32_t), st));
+  if (isd && (!isd_idx || !isd_fr || b)) return RB_ERR_INVALID_ARG;  // impulses apply to a single input
+  if (!a || !len || !out || !state) return RB_ERR_INVALID_ARG;
+  RB_CUDA(cudaMemsetAsync(state, 0, (size_t)B * sizeof(uint2), st));
   StreamArgs s;
   s.ld = ld;
   s.ntiles = stream_tiles_for(ld);
   s.always = always;
-  s.mask_ld = mask_ld;
   s.isd_idx = isd_idx;
   s.isd_fr = isd_fr;
   s.g_sd = g_sd;
-  const int per = max(1, (int)(0x7fffffff / (long long)s.ntiles));  // utterances per launch (grid.x < 2^31)
+  const int per = max(1, (int)(0x7fffffff / (long long)(s.ntiles + 1)));  // utterances per launch (grid.x < 2^31)
   for (int b0 = 0; b0 < B; b0 += per) {
     const int nb = min(per, B - b0);
     s.a = a + (size_t)b0 * ld;
     s.b = b ? b + (size_t)b0 * ld : nullptr;
     s.len = len + b0;
-    s.mask = mask ? mask + (size_t)b0 * mask_ld : nullptr;
     s.isd_off = isd ? isd_off + b0 : nullptr;
     s.out = out + (size_t)b0 * ld;
-    s.tile_peak = tile_peak + (size_t)b0 * s.ntiles;
-    s.counters = counters + b0;
-    const unsigned grid = (unsigned)nb * (unsigned)s.ntiles;
+    s.state = (uint2*)state + b0;
+    const unsigned grid = (unsigned)nb * (unsigned)(s.ntiles + 1);
     if (isd) norm_stream_kernel<true, false><<<grid, kSThreads, 0, st>>>(s);
     else if (b) norm_stream_kernel<false, true><<<grid, kSThreads, 0, st>>>(s);
     else norm_stream_kernel<false, false><<<grid, kSThreads, 0, st>>>(s);

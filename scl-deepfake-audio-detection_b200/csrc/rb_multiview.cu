@@ -19,13 +19,20 @@ namespace {
 // out_len[g] = (first_len < length && !repeat_pad) ? first_len : length
 // sample k of view v of group g:  m = start + k (mod first_len when view 0 is tiled);  value = m < len_v ? view[m]
 //                                 : (repeat_pad ? view[m mod len_v] : 0)
+// View v of group g lives in row r = view_row[g*V + v] of `views` (r >= 0) or in row -1 - r of `views_b` (r < 0); without a row
+// table the views are the rows g*V + v of `views`. Both sources share the row stride and the per-row lengths (RawBoost keeps
+// an utterance's length), so an item's original and augmented waveforms are read where they already are.
 template <int LAYOUT>  // 0: [G][length][V] (Dataset layout)   1: [G][V][length] (model layout)
 __global__ void __launch_bounds__(256)
-multiview_kernel(const float* __restrict__ views, const int32_t* __restrict__ len_arr, int V, int ld,
-                 const int32_t* __restrict__ start_arr, int length, int repeat_pad, float* __restrict__ out,
-                 int32_t* __restrict__ out_len) {
+multiview_kernel(const float* __restrict__ views, const float* __restrict__ views_b, const int32_t* __restrict__ view_row,
+                 const int32_t* __restrict__ len_arr, int V, int ld, const int32_t* __restrict__ start_arr, int length, int repeat_pad,
+                 float* __restrict__ out, int32_t* __restrict__ out_len, const float* __restrict__ view_label,
+                 float* __restrict__ labels) {
   const int g = blockIdx.y;
-  const int first_len = len_arr[(size_t)g * V];
+  auto row_of = [&](int v) { return view_row ? view_row[(size_t)g * V + v] : (int)((size_t)g * V + v); };
+  auto len_of = [&](int r) { return len_arr[r >= 0 ? r : -1 - r]; };
+  const int first_len = len_of(row_of(0));
+  if (labels && blockIdx.x == 0 && threadIdx.x < V) labels[(size_t)g * V + threadIdx.x] = view_label[threadIdx.x];
   const bool tile_first = first_len < length && repeat_pad;
   const int olen = (first_len < length && !repeat_pad) ? first_len : length;
   const int start = (first_len < length) ? 0 : start_arr[g];
@@ -40,13 +47,15 @@ multiview_kernel(const float* __restrict__ views, const int32_t* __restrict__ le
       v = (int)(e / olen);
       k = (int)(e - (size_t)v * olen);
     }
-    const int lv = len_arr[(size_t)g * V + v];
+    const int r = row_of(v);
+    const int lv = len_of(r);
+    const float* src = r >= 0 ? views + (size_t)r * ld : views_b + (size_t)(-1 - r) * ld;
     int m = start + k;
     if (tile_first && first_len > 0) m %= first_len;
     float val = 0.f;
     if (lv > 0) {
-      if (m < lv) val = __ldg(views + ((size_t)g * V + v) * ld + m);
-      else if (repeat_pad) val = __ldg(views + ((size_t)g * V + v) * ld + (m % lv));
+      if (m < lv) val = __ldg(src + m);
+      else if (repeat_pad) val = __ldg(src + (m % lv));
     }
     if (LAYOUT == 0) out[((size_t)g * length + k) * V + v] = val;
     else out[((size_t)g * V + v) * length + k] = val;
@@ -58,24 +67,35 @@ multiview_kernel(const float* __restrict__ views, const int32_t* __restrict__ le
 
 using namespace rb;
 
-extern "C" int rb_multiview_assemble(const float* views, const int32_t* len, int G, int V, int ld, const int32_t* start, int length,
-                                     int repeat_pad, int layout, float* out, int32_t* out_len, void* stream) {
+extern "C" int rb_multiview_assemble_ex(const float* views, const float* views_b, const int32_t* view_row, const int32_t* len, int G,
+                                        int V, int ld, const int32_t* start, int length, int repeat_pad, int layout, float* out,
+                                        int32_t* out_len, const float* view_label, float* labels, void* stream) {
   if (G < 0 || V < 0 || ld < 0 || length < 0 || (layout != 0 && layout != 1)) return RB_ERR_INVALID_ARG;
   if (G == 0 || V == 0 || length == 0) return RB_OK;
   if (!views || !len || !start || !out) return RB_ERR_INVALID_ARG;
+  if ((labels != nullptr) != (view_label != nullptr) || (labels && V > 256)) return RB_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t per_group = (size_t)length * V;
   const int bx = (int)std::min<size_t>((per_group + 255) / 256, 1184);  // 8 CTAs per SM cover one group; grid-stride beyond
   for (int g0 = 0; g0 < G; g0 += 65535) {
     const int ng = std::min(65535, G - g0);
     const dim3 grid(bx, ng);
-    const float* vw = views + (size_t)g0 * V * ld;
-    const int32_t* ln = len + (size_t)g0 * V;
+    // without a row table the group's rows are consecutive in `views`; with one, the table holds absolute rows
+    const float* vw = view_row ? views : views + (size_t)g0 * V * ld;
+    const int32_t* ln = view_row ? len : len + (size_t)g0 * V;
+    const int32_t* vr = view_row ? view_row + (size_t)g0 * V : nullptr;
     float* o = out + (size_t)g0 * per_group;
     int32_t* ol = out_len ? out_len + g0 : nullptr;
-    if (layout == 0) multiview_kernel<0><<<grid, 256, 0, st>>>(vw, ln, V, ld, start + g0, length, repeat_pad, o, ol);
-    else multiview_kernel<1><<<grid, 256, 0, st>>>(vw, ln, V, ld, start + g0, length, repeat_pad, o, ol);
+    float* lb = labels ? labels + (size_t)g0 * V : nullptr;
+    if (layout == 0) multiview_kernel<0><<<grid, 256, 0, st>>>(vw, views_b, vr, ln, V, ld, start + g0, length, repeat_pad, o, ol, view_label, lb);
+    else multiview_kernel<1><<<grid, 256, 0, st>>>(vw, views_b, vr, ln, V, ld, start + g0, length, repeat_pad, o, ol, view_label, lb);
     RB_LAUNCH_CHECK();
   }
   return RB_OK;
+}
+
+extern "C" int rb_multiview_assemble(const float* views, const int32_t* len, int G, int V, int ld, const int32_t* start, int length,
+                                     int repeat_pad, int layout, float* out, int32_t* out_len, void* stream) {
+  return rb_multiview_assemble_ex(views, nullptr, nullptr, len, G, V, ld, start, length, repeat_pad, layout, out, out_len, nullptr,
+                                  nullptr, stream);
 }

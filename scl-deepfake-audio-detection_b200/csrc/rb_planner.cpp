@@ -375,7 +375,8 @@ void draw_utt(Mt& rng, const Args& a, int algo, int length, UttDraw& out, float*
   }
   if (isd) {
     const double beta = rng.uniform(0.0, a.P);
-    const int n = (int)(length * (beta / 100));
+    // numpy slices the permutation with [:n], which clips at the array's length (reachable with P > 100)
+    const int n = std::min(std::max((int)(length * (beta / 100)), 0), length);
     out.isd_idx.resize(n);
     out.isd_fr.resize(n);
     if (length <= 65536) {  // 16-bit permutation array: half the cache footprint of the Fisher-Yates walk
@@ -477,6 +478,17 @@ int rb_planner_draw(rb_planner* p, const rb_args* args, int algo, int B, int ld,
                     rb_rng_state* state, rb_plan* view) {
   if (!p || !args || !view || B < 0 || ld < 0 || (B > 0 && !len)) return RB_ERR_INVALID_ARG;
   if (!seeds && !state) return RB_ERR_INVALID_ARG;
+  {  // what the reference's own calls would reject or what has no numpy equivalent here: refuse instead of throwing
+    const bool use_filters = (algo == 1 || algo == 3 || algo == 4 || algo == 5 || algo == 6 || algo == 7 || algo == 8) && algo != 2;
+    const bool use_isd = (algo == 2 || algo == 4 || algo == 5 || algo == 7 || algo == 8);
+    if (use_filters) {
+      const double cmin = std::min(args->minCoeff, args->maxCoeff), cmax = std::max(args->minCoeff, args->maxCoeff);
+      if (args->nBands < 1 || args->nBands > 1000 || !(cmin >= 1.0) || !(cmax <= 1e6) || !(args->fs > 0.0)) return RB_ERR_UNSUPPORTED;
+      if ((algo == 1 || algo == 4 || algo == 5 || algo == 6 || algo == 8) && (args->N_f < 1 || args->N_f > 1000)) return RB_ERR_UNSUPPORTED;
+    }
+    if (use_isd && !(args->P >= 0.0)) return RB_ERR_UNSUPPORTED;  // a negative count would mean numpy's "all but the last |n|"
+  }
+  try {
   Args a;
   a.N_f = args->N_f;
   a.nBands = args->nBands;
@@ -511,14 +523,20 @@ int rb_planner_draw(rb_planner* p, const rb_args* args, int algo, int B, int ld,
   }
   if (seeds) {
     std::atomic<int> next{0};
+    std::atomic<int> failed{0};
     auto work = [&]() {
-      Mt rng;
-      Scratch sc;
-      for (;;) {
-        const int u = next.fetch_add(1);
-        if (u >= B) break;
-        rng.seed(seeds[u]);
-        draw_utt(rng, a, algo, len[u], p->draws[u], ssi ? p->ssi_noise.p + (size_t)u * ld : nullptr, sc);
+      try {
+        Mt rng;
+        Scratch sc;
+        for (;;) {
+          const int u = next.fetch_add(1);
+          if (u >= B) break;
+          rng.seed(seeds[u]);
+          draw_utt(rng, a, algo, len[u], p->draws[u], ssi ? p->ssi_noise.p + (size_t)u * ld : nullptr, sc);
+        }
+      } catch (...) {  // an exception escaping a std::thread would terminate the process
+        failed.store(1);
+        next.store(B);
       }
     };
     const int nt = std::max(1, std::min(p->threads, B));
@@ -526,6 +544,7 @@ int rb_planner_draw(rb_planner* p, const rb_args* args, int algo, int B, int ld,
     for (int t = 1; t < nt; ++t) pool.emplace_back(work);
     work();
     for (auto& t : pool) t.join();
+    if (failed.load()) return RB_ERR_INVALID_ARG;
   } else {
     Mt rng;
     rng.adopt(state->key, state->pos, state->has_gauss, state->cached_gaussian);
@@ -594,6 +613,9 @@ int rb_planner_draw(rb_planner* p, const rb_args* args, int algo, int B, int ld,
     view->ssi_snr_db = p->ssi_snr.p;
   }
   return RB_OK;
+  } catch (...) {  // std::bad_alloc / std::length_error from the scratch vectors: no C++ exception crosses the C ABI
+    return RB_ERR_INVALID_ARG;
+  }
 }
 
 }  // extern "C"

@@ -139,6 +139,8 @@ class Engine:
         tensor is allocated here, untouched when ``out`` is passed."""
         self._check_batch(x, lengths)
         B, ld = x.shape
+        if plan is not None and (plan.B != B or plan.ld != ld):  # CSR offsets and the SSI noise rows are laid out for (B, ld)
+            raise ValueError(f"plan was packed for B={plan.B}, ld={plan.ld}; the batch is B={B}, ld={ld}")
         if out is None:
             out = torch.zeros_like(x)
         ws = self.workspace(B, ld, algo)
@@ -191,6 +193,8 @@ class Engine:
         if x.dtype != np.float32 or x.ndim != 2 or not x.flags.c_contiguous:
             raise ValueError("x must be a C-contiguous [B, ld] float32 array")
         B, ld = x.shape
+        if plan is not None and (plan.B != B or plan.ld != ld):
+            raise ValueError(f"plan was packed for B={plan.B}, ld={plan.ld}; the batch is B={B}, ld={ld}")
         if out is None:
             out = np.zeros_like(x)
         s = _lib.RbPlan()
@@ -263,6 +267,56 @@ class Engine:
         _lib.check(rc, f"rb_submit_host_seeded(algo={algo})")
         return int(ticket.value)
 
+    def submit_host_ex(self, algo: int, x: np.ndarray, dtype: str, lengths: np.ndarray, seeds: np.ndarray, sr, args, out) -> int:
+        """General streaming submit (``rb_submit_seeded_ex``) for host input: ``dtype`` "f32" (float32 waveforms) or "pcm16"
+        (int16 samples as a wav file holds them; converted on the device as sample / 32768, which is what ``librosa.load``
+        returns for 16-bit audio). ``out``: a host float32 array [B, ld] or a device tensor [B, ld] -- then the results stay on
+        the device and nothing is copied back. Returns a ticket for :meth:`wait_host`; buffers must stay alive until then."""
+        want = np.int16 if dtype == "pcm16" else np.float32
+        if x.dtype != want or x.ndim != 2 or not x.flags.c_contiguous:
+            raise ValueError(f"x must be a C-contiguous [B, ld] {np.dtype(want).name} array")
+        if lengths.dtype != np.int32 or seeds.dtype != np.uint32 or not lengths.flags.c_contiguous or not seeds.flags.c_contiguous:
+            raise ValueError("lengths must be a contiguous int32 array and seeds a contiguous uint32 array")
+        B, ld = x.shape
+        if torch.is_tensor(out):
+            if out.device != self.device or out.dtype != torch.float32 or tuple(out.shape) != (B, ld) or not out.is_contiguous():
+                raise ValueError("a device sink must be a contiguous [B, ld] float32 tensor on the engine's device")
+            y_ptr, y_kind = out.data_ptr(), _lib.RB_IO_DEVICE_F32
+        else:
+            if out.dtype != np.float32 or out.shape != (B, ld) or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous [B, ld] float32 array")
+            y_ptr, y_kind = out.ctypes.data, _lib.RB_IO_HOST_F32
+        a = _lib.args_struct(args, sr)
+        ticket = C.c_uint64(0)
+        rc = self.lib.rb_submit_seeded_ex(self._host_ctx(), int(algo), C.byref(a), C.c_void_p(x.ctypes.data),
+                                          _lib.RB_IO_HOST_PCM16 if dtype == "pcm16" else _lib.RB_IO_HOST_F32,
+                                          C.c_void_p(lengths.ctypes.data), C.c_void_p(seeds.ctypes.data), B, ld, C.c_void_p(y_ptr), y_kind,
+                                          None, 0, C.byref(ticket))
+        _lib.check(rc, f"rb_submit_seeded_ex(algo={algo})")
+        return int(ticket.value)
+
+    def process_device_seeded(self, algo: int, x: torch.Tensor, lengths: torch.Tensor, seeds: torch.Tensor, sr, args,
+                              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Seeded batch that already lives on the device: plans drawn on the device chunk by chunk WHILE the previous chunk is
+        being filtered (the planner's latency-bound kernels run beside the FIR kernel on their own low-priority streams),
+        results left on the device. Ordered after the work queued on torch's current stream, which in turn waits for the
+        results: no host synchronisation. ``seeds``: int32 / uint32 device tensor (``np.random.seed(seeds[u])`` per utterance)."""
+        self._check_batch(x, lengths)
+        B, ld = x.shape
+        if out is None:
+            out = torch.zeros_like(x)
+        if seeds.device != self.device or seeds.numel() != B or seeds.element_size() != 4:
+            raise ValueError("seeds must be a 32-bit integer tensor [B] on the engine's device")
+        a = _lib.args_struct(args, sr)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ticket = C.c_uint64(0)
+        with torch.cuda.device(self.device):
+            rc = self.lib.rb_submit_seeded_ex(self._host_ctx(), int(algo), C.byref(a), C.c_void_p(x.data_ptr()), _lib.RB_IO_DEVICE_F32,
+                                              C.c_void_p(lengths.data_ptr()), C.c_void_p(seeds.data_ptr()), B, ld,
+                                              C.c_void_p(out.data_ptr()), _lib.RB_IO_DEVICE_F32, C.c_void_p(stream), 1, C.byref(ticket))
+        _lib.check(rc, f"rb_submit_seeded_ex(device, algo={algo})")
+        return out
+
     def wait_host(self, ticket: int = 0) -> None:
         """Block until the submitted call ``ticket`` (0: every submitted call) has delivered its results."""
         _lib.check(self.lib.rb_ctx_wait(self._host_ctx(), int(ticket)), "rb_ctx_wait")
@@ -303,8 +357,17 @@ class Engine:
 _default: dict = {}
 
 
-def default_engine(device: int = 0) -> Engine:
-    """Process-wide engine used by the per-utterance reference-style functions in :mod:`RawBoost`."""
+def default_device() -> int:
+    """The device every per-utterance drop-in function uses: ``RAWBOOST_B200_DEVICE`` (default 0), read in ONE place."""
+    import os
+    return int(os.environ.get("RAWBOOST_B200_DEVICE", "0"))
+
+
+def default_engine(device: Optional[int] = None) -> Engine:
+    """Process-wide engine used by the per-utterance reference-style functions in :mod:`RawBoost`, :mod:`multiview` and
+    :mod:`reverb` (``device`` None = :func:`default_device`)."""
+    if device is None:
+        device = default_device()
     eng = _default.get(device)
     if eng is None:
         eng = _default[device] = Engine(device)

@@ -23,6 +23,30 @@ _args_struct = _lib.args_struct
 _MT_STATE_BYTES = 624 * 4 + 4  # numpy's mt19937_state: uint32 key[624]; int pos (numpy/random/src/mt19937/mt19937.h)
 
 
+_direct_ok = None
+
+
+def _direct_exchange_ok() -> bool:
+    """One-time self-check of the assumption the direct state exchange rests on: that ``bitgen.ctypes.state_address`` points at
+    numpy's ``mt19937_state {uint32 key[624]; int pos;}``. A private generator is seeded, its state read through the public
+    ``.state`` property and through the raw address, and the two must agree -- before and after drawing. On any mismatch (a
+    numpy whose private layout changed) the slower public ``get_state`` / ``set_state`` path is used instead, for good."""
+    global _direct_ok
+    if _direct_ok is None:
+        try:
+            bg = np.random.MT19937(987654321)
+            ok = True
+            for _ in range(2):
+                st = bg.state["state"]
+                raw = (C.c_uint32 * 625).from_address(bg.ctypes.state_address)
+                ok = ok and np.array_equal(np.frombuffer(raw, dtype=np.uint32, count=624), st["key"]) and int(np.int32(raw[624])) == int(st["pos"])
+                bg.random_raw(700)  # crosses a block boundary: key and pos both change
+            _direct_ok = bool(ok)
+        except Exception:
+            _direct_ok = False
+    return _direct_ok
+
+
 def _view(ptr, n, dtype):
     if not ptr or n == 0:
         return np.zeros(0, dtype=dtype)
@@ -60,12 +84,16 @@ class NativePlanner:
             # Without SSI no normal is drawn, so the legacy Gaussian cache is neither read nor written and the 624 words + cursor
             # can be exchanged directly with the bit generator's own mt19937_state {uint32 key[624]; int pos;} under its
             # lock (np.random.get_state() / set_state() cost ~70 us each, more than the LnL draw itself).
-            direct = algo not in ALGO_USES_SSI and type(bitgen).__name__ == "MT19937"
+            direct = algo not in ALGO_USES_SSI and type(bitgen).__name__ == "MT19937" and _direct_exchange_ok()
             if direct:
                 bitgen.lock.acquire()
-                state_addr = bitgen.ctypes.state_address
-                C.memmove(C.byref(state), state_addr, _MT_STATE_BYTES)
-                state.has_gauss, state.cached_gaussian = 0, 0.0
+                try:
+                    state_addr = bitgen.ctypes.state_address
+                    C.memmove(C.byref(state), state_addr, _MT_STATE_BYTES)
+                    state.has_gauss, state.cached_gaussian = 0, 0.0
+                except BaseException:
+                    bitgen.lock.release()  # never leave numpy's global generator locked
+                    raise
             else:
                 name, key, pos, has_gauss, cached = np.random.get_state()
                 C.memmove(state.key, np.ascontiguousarray(key, dtype=np.uint32).ctypes.data, 624 * 4)
@@ -102,6 +130,44 @@ class NativePlanner:
             bp.ssi_taps = fin(_view(view.ssi_taps, int(bp.ssi_tap_off[-1]), np.float32))
             bp.ssi_snr_db = fin(_view(view.ssi_snr_db, B, np.float32))
         return bp
+
+    def self_check(self) -> None:
+        """Draw one short algo-4 utterance (LnL, ISD and SSI: every kind of draw) here and with the numpy calls themselves from
+        the same seed and demand identical integers, impulse gains, float32 taps / noise and the same stream state afterwards.
+        Raises :class:`RawBoostLibraryError` on any difference -- a numpy whose legacy generator changed must not silently
+        desynchronise everything drawn after a RawBoost call. The caller's global stream is left untouched."""
+        from types import SimpleNamespace
+        from . import plans as _plans
+        args = SimpleNamespace(N_f=2, nBands=2, minF=20, maxF=8000, minBW=100, maxBW=1000, minCoeff=10, maxCoeff=40, minG=0, maxG=0,
+                               minBiasLinNonLin=5, maxBiasLinNonLin=20, P=10, g_sd=2, SNRmin=10, SNRmax=40)
+        saved = np.random.get_state()
+        try:
+            problems = []
+            for algo in (4, 5):  # 5 goes through the direct state exchange, 4 (SSI) through get_state / set_state
+                np.random.seed(20240229)
+                want = _plans.pack([_plans.draw_for_algo(1500, 16000, args, algo)])
+                want_state = np.random.get_state()
+                np.random.seed(20240229)
+                got = self.draw([1500], 16000, args, algo, use_global_stream=True, copy=True)
+                got_state = np.random.get_state()
+                for name in ("lnl_tap_off", "isd_off", "isd_idx", "isd_fr", "ssi_tap_off", "ssi_snr_db"):
+                    w, g = getattr(want, name), getattr(got, name)
+                    if (w is None) != (g is None) or (w is not None and not np.array_equal(w, g)):
+                        problems.append(f"algo {algo}: {name}")
+                for name in ("lnl_taps", "ssi_taps", "ssi_noise"):
+                    w, g = getattr(want, name), getattr(got, name)
+                    if (w is None) != (g is None):
+                        problems.append(f"algo {algo}: {name}")
+                    elif w is not None and (w.shape != g.shape or not np.all(np.abs(w.astype(np.float64) - g) <= np.spacing(np.abs(w)).astype(np.float64))):
+                        problems.append(f"algo {algo}: {name}")
+                if not (np.array_equal(want_state[1], got_state[1]) and want_state[2:] == got_state[2:]):
+                    problems.append(f"algo {algo}: stream state after the call")
+        finally:
+            np.random.set_state(saved)
+        if problems:
+            raise _lib.RawBoostLibraryError(
+                f"native planner does not reproduce numpy {np.__version__}'s legacy random stream ({', '.join(problems)}); "
+                "set RAWBOOST_B200_PLANNER=numpy to draw with the numpy calls themselves")
 
     def close(self):
         if self._h is not None:

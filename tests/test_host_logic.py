@@ -379,3 +379,50 @@ def test_fir_kernel_sass_contract():
     if os.path.exists(log):
         regs = [int(r) for r in re.findall(r"Used (\d+) registers", open(log).read())]
         assert regs and max(regs) <= 128, f"more than 128 registers: fewer than 4 CTAs of 128 threads per SM ({regs})"
+
+
+def test_native_planner_self_check_and_state_layout_guard():
+    """The default planner of the drop-in verifies itself against numpy before its first use and leaves the global stream alone;
+    the raw-state exchange is only used when numpy's private layout is what it assumes."""
+    from scl_deepfake_audio_detection_b200 import native_planner as nplan
+    np.random.seed(4321)
+    before = np.random.get_state()
+    p = nplan.NativePlanner(threads=1, pinned=False)
+    p.self_check()
+    after = np.random.get_state()
+    assert np.array_equal(before[1], after[1]) and before[2:] == after[2:]
+    assert nplan._direct_exchange_ok() is True
+    # a layout mismatch must switch the exchange off, not corrupt the stream: simulate it
+    nplan._direct_ok = False
+    try:
+        from types import SimpleNamespace
+        from scl_deepfake_audio_detection_b200 import plans
+        args = SimpleNamespace(**{**dict(N_f=5, nBands=5, minF=20, maxF=8000, minBW=100, maxBW=1000, minCoeff=10, maxCoeff=100, minG=0, maxG=0,
+                                         minBiasLinNonLin=5, maxBiasLinNonLin=20, P=10, g_sd=2, SNRmin=10, SNRmax=40)})
+        np.random.seed(9)
+        got = p.draw([3000], 16000, args, 5, use_global_stream=True, copy=True)
+        s1 = np.random.get_state()
+        np.random.seed(9)
+        want = plans.pack([plans.draw_for_algo(3000, 16000, args, 5)])
+        s2 = np.random.get_state()
+        assert np.array_equal(got.isd_idx, want.isd_idx) and np.array_equal(s1[1], s2[1]) and s1[2:] == s2[2:]
+    finally:
+        nplan._direct_ok = None
+
+
+def test_native_planner_rejects_bad_arguments_instead_of_throwing():
+    """rb_planner_draw validates its arguments (no C++ exception may cross the C ABI) and clips like numpy's [:n] for P > 100."""
+    from types import SimpleNamespace
+    from scl_deepfake_audio_detection_b200 import _lib, native_planner as nplan
+    base = dict(N_f=5, nBands=5, minF=20, maxF=8000, minBW=100, maxBW=1000, minCoeff=10, maxCoeff=100, minG=0, maxG=0,
+                minBiasLinNonLin=5, maxBiasLinNonLin=20, P=10, g_sd=2, SNRmin=10, SNRmax=40)
+    p = nplan.NativePlanner(threads=2, pinned=False)
+    for bad in (dict(P=-5), dict(minCoeff=-3), dict(nBands=0), dict(N_f=0)):
+        with pytest.raises(_lib.RawBoostLibraryError):
+            p.draw([1000, 1200], 16000, SimpleNamespace(**{**base, **bad}), 5, seeds=[1, 2])
+    got = p.draw([1000], 16000, SimpleNamespace(**{**base, "P": 400}), 2, seeds=[3], copy=True)  # beta up to 400 %: n clipped to L
+    assert 0 <= got.isd_idx.shape[0] <= 1000 and len(set(got.isd_idx.tolist())) == got.isd_idx.shape[0]
+    np.random.seed(3)
+    from scl_deepfake_audio_detection_b200 import plans
+    want_idx, _ = plans.draw_isd(1000, 400)
+    assert np.array_equal(got.isd_idx, want_idx.astype(np.int32))
