@@ -191,7 +191,8 @@ RB_API int rb_planner_draw(rb_planner* planner, const rb_args* args, int algo, i
  * Tap counts, impulse counts / positions and the float64 impulse gains are bit-identical to numpy's; float32 taps and
  * SSI noise agree to 1 ulp. len / seeds are DEVICE arrays; `storage` is device memory of rb_devplan_bytes() bytes,
  * 256-byte aligned; *plan (a HOST struct) receives device pointers into it, valid after the stream reaches this point.
- * Limits (RB_ERR_UNSUPPORTED otherwise): ld <= 65536 when the algo uses ISD; cascades of at most 1024 taps. */
+ * Rows of any length (the permutation of rows beyond 65536 samples is walked in global memory).
+ * Limit (RB_ERR_UNSUPPORTED otherwise): cascades of at most 1024 taps (freqz's 1024-point path), stages of at most 255 taps. */
 RB_API size_t rb_devplan_bytes(const rb_args* args, int algo, int B, int ld);
 RB_API int rb_devplan_draw(const rb_args* args, int algo, int B, int ld, const int32_t* len, const uint32_t* seeds,
                            void* storage, size_t storage_bytes, rb_plan* plan, void* stream);

@@ -3,7 +3,7 @@
 
 TEST INFRASTRUCTURE. The reference is pure Python (no C sources to build), so its "binary" is CPython bytecode:
 
-* ``oracle/_ref/RawBoost.pyc``   <- ``py_compile`` of ``/root/reference/datautils/RawBoost.py`` (the seven operators);
+* ``oracle/_ref/RawBoost.bytecode`` (a .pyc under a name snapshot tools do not filter out) <- ``py_compile`` of ``/root/reference/datautils/RawBoost.py`` (the seven operators);
 * ``oracle/_ref/dispatch.marshal`` <- the code object of ``process_Rawboost_feature`` taken out of the compiled (never
   executed) loader module ``/root/reference/datautils/asvspoof_2019_augall_3.py:377-439`` -- the loader's module-level
   imports (librosa, soundfile, pydub, torchaudio ...) are therefore never needed.
@@ -33,7 +33,7 @@ def build() -> bool:
     if not (os.path.isfile(OPERATORS_SRC) and os.path.isfile(LOADER_SRC)):
         return False
     os.makedirs(OUT, exist_ok=True)
-    py_compile.compile(OPERATORS_SRC, cfile=os.path.join(OUT, "RawBoost.pyc"), doraise=True,
+    py_compile.compile(OPERATORS_SRC, cfile=os.path.join(OUT, "RawBoost.bytecode"), doraise=True,
                        invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     with open(LOADER_SRC) as f:
         module_code = compile(f.read(), LOADER_SRC, "exec")
@@ -47,7 +47,7 @@ def build() -> bool:
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(OUT, "RawBoost.pyc")) and os.path.isfile(os.path.join(OUT, "dispatch.marshal"))
+    return os.path.isfile(os.path.join(OUT, "RawBoost.bytecode")) and os.path.isfile(os.path.join(OUT, "dispatch.marshal"))
 
 
 _cache = None
@@ -64,7 +64,7 @@ def load():
         last_error = f"{OUT} not present"
         return None
     try:
-        loader = importlib.machinery.SourcelessFileLoader("_reference_RawBoost", os.path.join(OUT, "RawBoost.pyc"))
+        loader = importlib.machinery.SourcelessFileLoader("_reference_RawBoost", os.path.join(OUT, "RawBoost.bytecode"))
         spec = importlib.util.spec_from_loader("_reference_RawBoost", loader)
         ops = importlib.util.module_from_spec(spec)
         loader.exec_module(ops)

@@ -176,7 +176,7 @@ const char* rb_error_string(int code) {
     case RB_ERR_WORKSPACE: return "rawboost_b200: workspace missing or smaller than rb_workspace_bytes()";
     case RB_ERR_NO_DEVICE: return "rawboost_b200: no usable CUDA device (needs compute capability 10.0)";
     case RB_ERR_PLAN: return "rawboost_b200: a plan field required by this algo is NULL";
-    case RB_ERR_UNSUPPORTED: return "rawboost_b200: arguments outside what the device-side planner supports (ld <= 65536 with ISD, cascades <= 1024 taps)";
+    case RB_ERR_UNSUPPORTED: return "rawboost_b200: arguments outside what the planner supports (cascades <= 1024 taps and stages <= 255 taps on the device; nBands / N_f >= 1, P >= 0)";
     default: break;
   }
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -308,7 +308,8 @@ struct CallRes {
   char* planmem = nullptr;  // device-drawn plans of the whole batch (rb_process_host_seeded)
   size_t planmem_bytes = 0;
   std::vector<cudaEvent_t> ev_planned;  // one per chunk
-  cudaEvent_t ev_meta = nullptr, ev_body[3] = {nullptr, nullptr, nullptr}, ev_done = nullptr, ev_user = nullptr;
+  std::vector<cudaEvent_t> ev_body;     // one per planner piece
+  cudaEvent_t ev_meta = nullptr, ev_done = nullptr, ev_user = nullptr;
   bool inflight = false;
   uint64_t ticket = 0;
 };
@@ -479,19 +480,33 @@ int run_pipeline(rb_ctx* c, int algo, const IoSpec& io, const int32_t* len, int 
     }
   };
   mark(0, c->s_in);
-  // Device planner. The plans need only lengths and seeds. Its kernels are latency-bound (one warp per utterance) and are
-  // issued in three pieces -- chunk 0, chunk 1, everything else -- so that the first results leave early (the call is bound by
-  // the copy-out stream, which starts with the first filtered chunk).
+  // Device planner. The plans need only lengths and seeds. Its kernels are latency-bound (one warp per utterance: the stream
+  // replay of one utterance takes ~2 ms however few utterances a launch holds), so they are issued in pieces -- chunk 0,
+  // chunk 1, then about 4096 utterances at a time (one full wave of the replay kernel) -- so that the first results leave
+  // early (a host-buffer call is bound by the copy-out stream, which starts with the first filtered chunk) while large batches
+  // pay the replay latency once per wave, not once per chunk.
   //   plan_mode 0 (default): stream replay on s_plan, swap application on s_apply, both at low priority beside the kernels.
-  //   plan_mode 1: in line on the kernels' stream, each piece right before the first chunk that needs it; the planner then
-  //     never shares an SM with the FIR-bank kernel. Slower (the planner's latency-bound kernels leave the SMs mostly idle
-  //     while nothing else may run); kept for measurement.
-  int piece_end[3] = {nchunks, nchunks, nchunks};
-  int npieces = 1;
+  //     Measured (scripts/gpu_overlap_probe.py): while the FIR-bank kernel still has CTAs to dispatch, the hardware does not
+  //     place another kernel's CTAs in the registers / shared memory its resident CTAs leave free, so the planner really runs
+  //     in the gaps: during copies, at the tail of each FIR launch, and before the first chunk.
+  //   plan_mode 1: in line on the kernels' stream, each piece right before the first chunk that needs it; kept for measurement.
+  std::vector<int> piece_end;
   if (devplan && !use_ssi && nchunks >= 3) {  // SSI tap offsets need the stream positions of every utterance: one piece
-    npieces = 3;
-    piece_end[0] = 1;
-    piece_end[1] = 2;
+    const int per_wave = std::max(1, 4096 / chunk);
+    if (!x_dev) {
+      piece_end.push_back(1);
+      piece_end.push_back(2);
+    }
+    while ((piece_end.empty() ? 0 : piece_end.back()) < nchunks)
+      piece_end.push_back(std::min(nchunks, (piece_end.empty() ? 0 : piece_end.back()) + per_wave));
+  } else {
+    piece_end.push_back(nchunks);
+  }
+  const int npieces = (int)piece_end.size();
+  while (devplan && (int)R.ev_body.size() < npieces) {
+    cudaEvent_t e;
+    RB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    R.ev_body.push_back(e);
   }
   auto plan_piece = [&](int pc, cudaStream_t s_body, cudaStream_t s_swap) -> int {
     const int cb = pc ? piece_end[pc - 1] : 0;
@@ -679,7 +694,7 @@ int rb_ctx_create(rb_ctx** out, int device) {
   for (cudaStream_t* s : {&c->s_plan, &c->s_apply})
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(s, cudaStreamNonBlocking, prio_lo);
   for (CallRes& R : c->res)
-    for (cudaEvent_t* ev : {&R.ev_meta, &R.ev_body[0], &R.ev_body[1], &R.ev_body[2], &R.ev_done, &R.ev_user})
+    for (cudaEvent_t* ev : {&R.ev_meta, &R.ev_done, &R.ev_user})
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   for (Slot& sl : c->slot)
     for (cudaEvent_t* ev : {&sl.ev_in, &sl.ev_planned, &sl.ev_done, &sl.ev_out})
@@ -705,7 +720,8 @@ int rb_ctx_destroy(rb_ctx* c) {
     if (R.meta) cudaFree(R.meta);
     if (R.planmem) cudaFree(R.planmem);
     for (cudaEvent_t e : R.ev_planned) cudaEventDestroy(e);
-    for (cudaEvent_t e : {R.ev_meta, R.ev_body[0], R.ev_body[1], R.ev_body[2], R.ev_done, R.ev_user})
+    for (cudaEvent_t e : R.ev_body) cudaEventDestroy(e);
+    for (cudaEvent_t e : {R.ev_meta, R.ev_done, R.ev_user})
       if (e) cudaEventDestroy(e);
   }
   for (cudaStream_t s : {c->s_in, c->s_plan, c->s_apply, c->s_cmp, c->s_out})

@@ -38,6 +38,7 @@ namespace rb {
 namespace {
 
 constexpr int kMtN = 624, kMtM = 397;
+constexpr int kNarrowMax = 65536;  // longest row whose permutation is held as uint16 in shared memory
 constexpr uint32_t kFull = 0xffffffffu;
 
 // ---- MT19937, one warp per stream, state and two tempered blocks in shared memory ------------------------------------
@@ -283,7 +284,8 @@ scan_kernel(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ off) {
 constexpr int kDupWords = 128;  // 4096-bit duplicate filter per warp (keeps 7 CTAs = 28 utterances per SM)
 constexpr int kBodyWarps = 4;  // 30 KB of MT19937 state per CTA: up to 7 CTAs = 28 utterances in flight per SM
 
-__device__ void shuffle_scan_warp(MtStream& s, int L, uint16_t* __restrict__ jseq, uint32_t* __restrict__ cuts, uint32_t* dupset,
+template <typename JT>  // uint16_t for rows of at most 65536 samples, uint32_t beyond
+__device__ void shuffle_scan_warp(MtStream& s, int L, JT* __restrict__ jseq, uint32_t* __restrict__ cuts, uint32_t* dupset,
                                   int lane) {
   const uint32_t lt = (1u << lane) - 1u;
   int i = L - 1;
@@ -308,7 +310,7 @@ __device__ void shuffle_scan_warp(MtStream& s, int L, uint16_t* __restrict__ jse
       const int R = i - lo + 1;                                  // steps left under this mask
       const uint32_t in_region = __ballot_sync(kFull, A < R);    // a prefix of the lanes: the words this mask consumes
       const bool valid = ((acc >> lane) & 1u) && (A < R);
-      if (valid) jseq[(L - 1) - (i - A)] = (uint16_t)v;
+      if (valid) jseq[(L - 1) - (i - A)] = (JT)v;
       i -= __popc(acc & in_region);
       s.advance(__popc(in_region), lane);
     }
@@ -351,7 +353,7 @@ __device__ void shuffle_scan_warp(MtStream& s, int L, uint16_t* __restrict__ jse
         int start = 0;
         for (;;) {
           const bool active = valid && lane >= start;
-          const uint32_t same = __match_any_sync(kFull, active ? (uint32_t)j : (0x10000u + (uint32_t)lane));
+          const uint32_t same = __match_any_sync(kFull, active ? (uint32_t)j : (0x80000000u + (uint32_t)lane));
           uint32_t tbit = 0;
           if (active && j > i0 - 32 && j != i0 - lane) tbit = 1u << (i0 - j);
           const uint32_t tmap = __reduce_or_sync(kFull, tbit);
@@ -366,9 +368,10 @@ __device__ void shuffle_scan_warp(MtStream& s, int L, uint16_t* __restrict__ jse
   }
 }
 
+template <typename JT>
 __global__ void __launch_bounds__(32 * kBodyWarps)
 plan_body_kernel(rb_args a, int algo, int B, int ld, int jld, const int32_t* __restrict__ len_arr,
-                 const uint32_t* __restrict__ seeds, const int32_t* __restrict__ isd_off, double* __restrict__ isd_fr, uint16_t* __restrict__ jseq_all,
+                 const uint32_t* __restrict__ seeds, const int32_t* __restrict__ isd_off, double* __restrict__ isd_fr, JT* __restrict__ jseq_all,
                  uint32_t* __restrict__ cuts_all, int cuts_ld, float* __restrict__ ssi_noise, double* __restrict__ ssi_params,
                  int32_t* __restrict__ ssi_cnt, float* __restrict__ ssi_snr) {
   __shared__ MtSmem msm[kBodyWarps];
@@ -585,6 +588,65 @@ perm_apply_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uin
   for (int k = lane; k < n; k += 32) isd_idx[beg + k] = (int32_t)(k < live ? perm[k] : __ldcg(state + k));
 }
 
+// ---- the swaps for rows longer than 65536 samples ------------------------------------------------------------------------
+// Un-cropped utterances (the loaders apply RawBoost before the crop, asvspoof_2019_augall_3.py:105-117) run to ~200 k samples:
+// the permutation no longer fits shared memory as uint16. It then lives in global memory as uint32 (L2 for the most part) and
+// one warp per utterance applies the same conflict-free groups with L2 round trips instead of shared-memory ones. The walk is
+// latency-bound (about one L2 round trip per 32 steps) but every utterance has its own warp, 32 warps per SM, so a batch of
+// long rows still takes a small fraction of the time the FIR bank needs for them.
+constexpr int kWideWarps = 4;
+
+__global__ void __launch_bounds__(32 * kWideWarps)
+perm_apply_wide_kernel(int B, int jld, const int32_t* __restrict__ len_arr, const uint32_t* __restrict__ jseq_all,
+                       const uint32_t* __restrict__ cuts_all, int cuts_ld, const int32_t* __restrict__ isd_off,
+                       int32_t* __restrict__ isd_idx, uint32_t* __restrict__ state_all) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x * kWideWarps + warp;
+  if (u >= B) return;
+  const int L = len_arr[u];
+  const int beg = isd_off[u], n = isd_off[u + 1] - beg;
+  if (n <= 0) return;  // no impulse: nothing of the permutation is used
+  const uint32_t* __restrict__ jseq = jseq_all + (size_t)u * jld;
+  const uint32_t* __restrict__ cuts = cuts_all + (size_t)u * cuts_ld;
+  uint32_t* perm = state_all + (size_t)u * jld;
+  for (int k = lane; k < L; k += 32) __stcg(perm + k, (uint32_t)k);
+  __syncwarp();
+  const int nsteps = max(L - 1, 0);
+  const int nch = (nsteps + 31) >> 5;
+  uint32_t jn = (lane < nsteps) ? __ldcg(jseq + lane) : 0u;
+  uint32_t cn = nch > 0 ? __ldcg(cuts) : 0u;
+  for (int c = 0; c < nch; ++c) {
+    const uint32_t j = jn;
+    uint32_t cut = cn;
+    const int k = c * 32 + lane;
+    const bool valid = k < nsteps;
+    if (c + 1 < nch) {  // next chunk's targets and group mask travel while this chunk is applied
+      jn = (k + 32 < nsteps) ? __ldcg(jseq + k + 32) : 0u;
+      cn = __ldcg(cuts + c + 1);
+    }
+    uint32_t* slotp = perm + ((L - 1) - k);
+    int s0 = 0;
+    for (;;) {
+      const int s1 = cut ? __ffs(cut) - 1 : 32;
+      const bool doit = valid && lane >= s0 && lane < s1;
+      uint32_t va = 0u, vb = 0u;
+      if (doit) {
+        va = __ldcg(perm + j);
+        vb = __ldcg(slotp);
+      }
+      if (doit) {
+        __stcg(perm + j, vb);
+        __stcg(slotp, va);
+      }
+      __syncwarp();
+      if (!cut) break;
+      cut &= cut - 1;
+      s0 = s1;
+    }
+  }
+  for (int k = lane; k < n; k += 32) isd_idx[beg + k] = (int32_t)__ldcg(perm + k);
+}
+
 // ---- genNotchCoeffs arithmetic (RawBoost.py:37-47), one CTA per filter, float64 -------------------------------------------
 constexpr int kDesignThreads = 128;
 constexpr int kDesignMaxK = 1024;   // freqz's 1024-point FFT path; longer cascades are refused by the host entry
@@ -725,9 +787,10 @@ DevPlanLayout layout(const rb_args& a, int algo, int B, int ld) {
   l.isd_fr = take(nmax * 8);
   l.jld = (int)align_up((size_t)ld, kStageSteps);  // rows padded to whole staging pieces of perm_apply_kernel
   l.cuts_ld = l.jld / 32;
-  l.isd_jseq = take(isd ? (size_t)B * l.jld * 2 : 0);
+  const size_t jbytes = ld > kNarrowMax ? 4 : 2;   // swap targets / permutation entries: uint16 up to 65536 samples, uint32 beyond
+  l.isd_jseq = take(isd ? (size_t)B * l.jld * jbytes : 0);
   l.isd_cuts = take(isd ? (size_t)B * l.cuts_ld * 4 : 0);
-  l.isd_state = take(isd ? (size_t)B * l.jld * 2 : 0);
+  l.isd_state = take(isd ? (size_t)B * l.jld * jbytes : 0);
   l.ssi_noise = take(ssi ? (size_t)B * ld * 4 : 0);
   l.ssi_params = take(ssi ? (size_t)B * stride * 8 : 0);
   l.ssi_cnt = take(ssi ? (size_t)B * 4 : 0);
@@ -788,7 +851,7 @@ int devplan_begin(const rb_args* args, int algo, int B, int ld, const int32_t* l
   if (B == 0 || ld == 0 || !(lnl || isd || ssi)) return RB_OK;
   if (!len || !seeds) return RB_ERR_INVALID_ARG;
   if (!args_ok(*args)) return RB_ERR_UNSUPPORTED;
-  if (isd && ld > 65536) return RB_ERR_UNSUPPORTED;  // the permutation lives in shared memory as uint16
+  if (isd && ld > (1 << 30)) return RB_ERR_UNSUPPORTED;
   if (ld % 4 != 0) return RB_ERR_ALIGNMENT;
   if (!storage || ((uintptr_t)storage & 255u)) return storage ? RB_ERR_ALIGNMENT : RB_ERR_WORKSPACE;
   const DevPlanLayout l = layout(*args, algo, B, ld);
@@ -832,11 +895,19 @@ int devplan_body(const rb_args* args, int algo, int B, int ld, const int32_t* le
   const DevPlanLayout l = layout(*args, algo, B, ld);
   char* d = (char*)storage;
   const size_t stride = 3 * (size_t)args->nBands + 1;
-  plan_body_kernel<<<(count + kBodyWarps - 1) / kBodyWarps, 32 * kBodyWarps, 0, st>>>(
-      *args, algo, count, ld, l.jld, len + first, seeds + first, (const int32_t*)(d + l.isd_off) + first, (double*)(d + l.isd_fr),
-      (uint16_t*)(d + l.isd_jseq) + (size_t)first * l.jld, (uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld,
-      (float*)(d + l.ssi_noise) + (size_t)first * ld, (double*)(d + l.ssi_params) + (size_t)first * stride,
-      (int32_t*)(d + l.ssi_cnt) + first, (float*)(d + l.ssi_snr) + first);
+  const unsigned grid = (count + kBodyWarps - 1) / kBodyWarps;
+  if (ld > kNarrowMax)
+    plan_body_kernel<uint32_t><<<grid, 32 * kBodyWarps, 0, st>>>(
+        *args, algo, count, ld, l.jld, len + first, seeds + first, (const int32_t*)(d + l.isd_off) + first, (double*)(d + l.isd_fr),
+        (uint32_t*)(d + l.isd_jseq) + (size_t)first * l.jld, (uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld,
+        (float*)(d + l.ssi_noise) + (size_t)first * ld, (double*)(d + l.ssi_params) + (size_t)first * stride,
+        (int32_t*)(d + l.ssi_cnt) + first, (float*)(d + l.ssi_snr) + first);
+  else
+    plan_body_kernel<uint16_t><<<grid, 32 * kBodyWarps, 0, st>>>(
+        *args, algo, count, ld, l.jld, len + first, seeds + first, (const int32_t*)(d + l.isd_off) + first, (double*)(d + l.isd_fr),
+        (uint16_t*)(d + l.isd_jseq) + (size_t)first * l.jld, (uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld,
+        (float*)(d + l.ssi_noise) + (size_t)first * ld, (double*)(d + l.ssi_params) + (size_t)first * stride,
+        (int32_t*)(d + l.ssi_cnt) + first, (float*)(d + l.ssi_snr) + first);
   RB_LAUNCH_CHECK();
   return RB_OK;
 }
@@ -848,6 +919,14 @@ int devplan_apply(const rb_args* args, int algo, int B, int ld, const int32_t* l
   if (!isd || count <= 0) return RB_OK;
   const DevPlanLayout l = layout(*args, algo, B, ld);
   char* d = (char*)storage;
+  if (ld > kNarrowMax) {
+    perm_apply_wide_kernel<<<(count + kWideWarps - 1) / kWideWarps, 32 * kWideWarps, 0, st>>>(
+        count, l.jld, len + first, (const uint32_t*)(d + l.isd_jseq) + (size_t)first * l.jld,
+        (const uint32_t*)(d + l.isd_cuts) + (size_t)first * l.cuts_ld, l.cuts_ld, (const int32_t*)(d + l.isd_off) + first,
+        (int32_t*)(d + l.isd_idx), (uint32_t*)(d + l.isd_state) + (size_t)first * l.jld);
+    RB_LAUNCH_CHECK();
+    return RB_OK;
+  }
   static const int kPhaseT[5] = {65536, 49152, 32768, 16384, 0};
   RB_CUDA(cudaFuncSetAttribute(perm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   RB_CUDA(cudaFuncSetAttribute(perm_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -534,6 +534,9 @@ int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const flo
     auto kernel = tail.mode == TAIL_AFFINE ? fir_bank_kernel<TAIL_AFFINE>
                   : tail.mode == TAIL_SSI  ? fir_bank_kernel<TAIL_SSI>
                                            : fir_bank_kernel<TAIL_NONE>;
+    // Largest shared-memory carve-out: the kernel itself needs little L1, and the device planner's kernels (up to ~100 KB of
+    // shared memory per CTA) can then run in what the four FIR CTAs of an SM leave free instead of waiting for them.
+    RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kernel<<<grid, kThreads, 0, st>>>(x + (size_t)b0 * ld, len + b0, ld, taps, tap_off + (size_t)b0 * n_f, n_f, pow_base, pow_step,
                                        y + (size_t)b0 * ld, stats ? stats + (size_t)b0 * ntiles * kStatN : nullptr,
                                        mask ? mask + (size_t)b0 * mask_ld : nullptr, mask_ld, tail.shifted(b0, ld));

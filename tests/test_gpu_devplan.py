@@ -17,7 +17,7 @@ torch = pytest.importorskip("torch")
 from oracle import rawboost_oracle as orc  # noqa: E402  (checker only)
 
 ARGS = orc.make_args()
-RAGGED = [1, 2, 3, 31, 32, 33, 34, 37, 63, 64, 65, 600, 1023, 1024, 1025, 2560, 2561, 4097, 16000, 40000, 65535, 65536]
+RAGGED = [1, 2, 3, 31, 32, 33, 34, 37, 63, 64, 65, 600, 1023, 1024, 1025, 2560, 2561, 4097, 16000, 40000, 49152, 49153, 65535, 65536]
 
 
 @pytest.fixture(scope="module")
@@ -100,13 +100,42 @@ def test_device_plan_nondefault_arguments(eng, P):
 
 
 def test_device_plan_unsupported_is_loud(eng):
-    """Utterances longer than 65536 samples with ISD are refused, not silently mis-drawn."""
+    """What the device planner does not implement is refused, not silently mis-drawn (cascades beyond freqz's 1024-point path)."""
     from scl_deepfake_audio_detection_b200 import _lib
-    ln = torch.tensor([70000], dtype=torch.int32, device="cuda")
+    ln = torch.tensor([7000], dtype=torch.int32, device="cuda")
     with pytest.raises(_lib.RawBoostLibraryError):
-        eng.draw_device_plan(ln, [1], 16000, ARGS, 5, 70000)
-    eng.draw_device_plan(ln, [1], 16000, ARGS, 1, 70000)  # LnL only: fine at any length
-    torch.cuda.synchronize()
+        eng.draw_device_plan(ln, [1], 16000, orc.make_args(nBands=12, maxCoeff=200), 5, 7000)
+
+
+@pytest.mark.parametrize("lengths", [[65537], [211000, 100000, 70001, 65537, 300, 64600], [49152, 49153, 50176, 50177, 65536]])
+def test_device_plan_long_rows_equal_numpy(eng, P, lengths):
+    """Un-cropped utterances (asvspoof_2019_augall_3.py:105-117 applies RawBoost before the crop): beyond 65536 samples the
+    permutation runs as uint32 in global memory, beyond 49152 its first steps do -- impulse positions must stay numpy's, bit
+    for bit, on both sides of both thresholds and in a ragged batch that mixes them."""
+    seeds = [4000 + 7 * u for u in range(len(lengths))]
+    for algo in (2, 5):
+        _, got, ld = device_plan(eng, lengths, seeds, algo)
+        ref = P.draw_batch(lengths, 16000, ARGS, algo, seeds=seeds, ld=ld)
+        assert np.array_equal(ref.isd_off, got.isd_off)
+        assert np.array_equal(ref.isd_idx, got.isd_idx), "impulse positions differ from numpy's permutation"
+        assert np.array_equal(ref.isd_fr, got.isd_fr)
+        if algo == 5:
+            assert np.array_equal(ref.lnl_tap_off, got.lnl_tap_off) and ulp_err(got.lnl_taps, ref.lnl_taps) <= 1.0
+
+
+def test_seeded_host_entry_long_rows(eng, P):
+    """The pipelined host entry on a ragged batch of long rows == the resident path on numpy-drawn plans."""
+    rs = np.random.RandomState(5)
+    lengths = [120000, 64600, 211000, 65537, 9]
+    waves = [(0.4 * rs.standard_normal(n)).astype(np.float32) for n in lengths]
+    seeds = [900 + u for u in range(len(lengths))]
+    for algo in (5, 2):
+        bp = P.draw_batch(lengths, 16000, ARGS, algo, seeds=seeds)
+        x, ln = eng.pack_waveforms(waves, ld=bp.ld)
+        ref = eng.process(algo, x, ln, eng.upload_plan(bp)).cpu().numpy()
+        got = eng.process_host_seeded(algo, x.cpu().numpy(), np.array(lengths, np.int32), np.array(seeds, np.uint32), 16000, ARGS)
+        for u, n in enumerate(lengths):
+            assert np.array_equal(got[u, :n], ref[u, :n]), (algo, u)
 
 
 @pytest.mark.parametrize("algo", [0, 1, 2, 3, 5, 8])
