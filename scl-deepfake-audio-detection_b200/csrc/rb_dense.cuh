@@ -16,7 +16,7 @@ int stream_tiles_for(int ld);
 
 // out = normWav(v, always) where v = a (+ b when b != NULL), or -- with isd_off != NULL (b must be NULL) --
 // out = normWav(a with the impulses applied, always). One streaming launch; see rb_dense.cu.
-// state: (B + 1) x 8 bytes of device scratch (zeroed here). out may equal a when b == NULL (in place: the copy is skipped).
+// state: B x 8 bytes of device scratch (zeroed here). out may equal a when b == NULL (in place: the copy is skipped).
 int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B, int ld, int always, const int32_t* isd_off,
                        const int32_t* isd_idx, const double* isd_fr, float g_sd, float* out, void* state, cudaStream_t st);
 
