@@ -240,7 +240,41 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
   const bool warp_active = tile0 + warp * kWarpSpan < len;  // warps whose outputs are all past the end only help staging
 
   int gbase = tile0 - kHalo;
-  stage_x(sm.x1, row, len, gbase);
+  // The first filter's taps are requested BEFORE the waveform tile, so that the two global round trips of a tile's start-up
+  // overlap instead of following each other (it matters for single short filters: ~1 us of ~5 us of fixed cost per tile).
+  // staged0: the first segment's taps are already in he / ho when the filter loop gets there.
+  bool staged0 = false;
+  {
+    const int t0 = tap_off[u * n_f];
+    const int K = tap_off[u * n_f + 1] - t0;
+    const int kseg = min(kSegTaps, K);
+    const int e = tile0 + ((K + 1) >> 1) - (K - 1) - gbase;
+    if (K > 0 && e >= 0 && e + kseg <= kMaxReach) {
+      const int z = e & 3;
+      const int ngroups = (z + kseg + 1 + 3) >> 2;
+      const int nbody = (ngroups + kBodyTaps / 4 - 1) / (kBodyTaps / 4);
+      constexpr int kPre = (kTapCap + kThreads - 1) / kThreads;  // taps per thread (5)
+      float tp[kPre];
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) {
+        const int i = tid + q * kThreads, m = i - z;
+        tp[q] = (i < nbody * kBodyTaps && m >= 0 && m < kseg) ? __ldg(taps + t0 + (K - 1 - m)) : 0.f;
+      }
+      stage_x(sm.x1, row, len, gbase);
+#pragma unroll
+      for (int q = 0; q < kPre; ++q) {
+        const int i = tid + q * kThreads;
+        if (i < nbody * kBodyTaps) {
+          sm.he[i] = tp[q];
+          if (i + 1 < nbody * kBodyTaps) sm.ho[i + 1] = tp[q];
+          if (i == 0) sm.ho[0] = 0.f;
+        }
+      }
+      staged0 = true;
+    } else {
+      stage_x(sm.x1, row, len, gbase);
+    }
+  }
 
   float2 acc[kR];
 #pragma unroll
@@ -259,7 +293,8 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       //   y[n] += sum_{i<kseg} h[i0+i] * xp[n + i + d],  d = shift - (K-1) + i0
       const int d = shift - (K - 1) + i0;
       int e = tile0 + d - gbase;
-      __syncthreads();  // previous segment done with he/ho/xp (and x1 staged on first pass)
+      const bool prestaged = staged0 && f == 0 && i0 == 0;
+      if (!prestaged) __syncthreads();  // previous segment done with he/ho/xp (and x1 staged on first pass)
       if (e < 0 || e + kseg > kMaxReach) {  // uniform: restage the samples around this segment
         gbase = (tile0 + d) & ~3;
         e = tile0 + d - gbase;
@@ -270,12 +305,14 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       const int z = e & 3;                                      // leading zero taps that align the window to 16 B
       const int ngroups = (z + kseg + 1 + 3) >> 2;              // 4-tap groups holding taps (+1: the odd-output copy is shifted)
       const int nbody = (ngroups + kBodyTaps / 4 - 1) / (kBodyTaps / 4);
-      for (int i = tid; i < nbody * kBodyTaps; i += kThreads) {
-        const int m = i - z;                                    // he[i] = h[i0 + m]
-        const float hv = (m >= 0 && m < kseg) ? __ldg(taps + t0 + (K - 1 - (i0 + m))) : 0.f;
-        sm.he[i] = hv;
-        if (i + 1 < nbody * kBodyTaps) sm.ho[i + 1] = hv;
-        if (i == 0) sm.ho[0] = 0.f;
+      if (!prestaged) {
+        for (int i = tid; i < nbody * kBodyTaps; i += kThreads) {
+          const int m = i - z;                                    // he[i] = h[i0 + m]
+          const float hv = (m >= 0 && m < kseg) ? __ldg(taps + t0 + (K - 1 - (i0 + m))) : 0.f;
+          sm.he[i] = hv;
+          if (i + 1 < nbody * kBodyTaps) sm.ho[i + 1] = hv;
+          if (i == 0) sm.ho[0] = 0.f;
+        }
       }
       const float* src = sm.x1;
       if (power != 1) {
@@ -478,7 +515,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
   } else {  // TAIL_SSI: out = x + coloured noise * scale  (RawBoost.py:95-96)
     const float scale = ssi_scale_block(ust, S_AUXSQ, ust, nact, tail.snr_db[u]);
     const float* arow = tail.aux + (size_t)u * ld;
-    constexpr int kU = 4;
+    constexpr int kU = 8;  // the accumulators are dead here: room for sixteen float4 in flight per thread (both reads come from L2)
     for (int c0 = tid; c0 < nchunk; c0 += kU * kThreads) {
       float4 v[kU], a[kU];
 #pragma unroll

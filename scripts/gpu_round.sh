@@ -1,13 +1,18 @@
-# full GPU check: tests, smoke, default bench, per-algo values, ncu evidence
-tag=${1:-r02v1}
+# Full GPU check of a build: parity tests, smoke, the bench line (all sub-records), the reference arm, sanitizers, ncu evidence.
+# usage (on the GPU box, via gpurun): bash scripts/gpu_round.sh <tag>      -> everything lands in gpurun_out/<tag>_*
+tag=${1:-r02}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -2 gpurun_out/smoke.log
-timeout 900 python bench.py > gpurun_out/${tag}_bench_default.json 2> gpurun_out/${tag}_bench_default.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/${tag}_bench_default.json
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2>&1; echo "ref rc=$?"; cut -c1-200 gpurun_out/${tag}_bench_reference.json
-bash scripts/gpu_algos.sh
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${tag}_pytest_gpu.log
+tail -3 gpurun_out/${tag}_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${tag}_smoke.log; tail -2 gpurun_out/${tag}_smoke.log
+timeout 1200 python bench.py > gpurun_out/${tag}_bench_default.json 2> gpurun_out/${tag}_bench_default.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/${tag}_bench_default.json
+timeout 900 python bench.py --impl reference > gpurun_out/${tag}_bench_reference.json 2>/dev/null; echo "ref rc=$?"; cut -c1-200 gpurun_out/${tag}_bench_reference.json
+timeout 300 python scripts/gpu_fir_sweep.py 2048 2>&1 | grep -v Warning > gpurun_out/${tag}_fir_sweep.log
+timeout 300 python scripts/gpu_isd_probe.py 4096 1024 2>&1 | grep -v Warning > gpurun_out/${tag}_stream_probe.log
+for tool in memcheck racecheck synccheck; do
+  echo "== compute-sanitizer --tool $tool python scripts/gpu_sanitize.py"
+  timeout 900 compute-sanitizer --tool $tool python scripts/gpu_sanitize.py 2>&1 | grep -E "sanitize script done|ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" | head -8
+done > gpurun_out/${tag}_compute_sanitizer.log 2>&1
 bash scripts/gpu_profile.sh $tag
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_devplan_launches.csv python scripts/gpu_devplan_time.py 5 4096 2 > /dev/null 2>&1
-python scripts/gpu_timeline.py 0 > gpurun_out/${tag}_timeline.log 2>&1; tail -9 gpurun_out/${tag}_timeline.log
-python scripts/gpu_config4.py 8192 5 > gpurun_out/${tag}_config4.json 2>&1; cut -c1-300 gpurun_out/${tag}_config4.json
+ls gpurun_out | grep ${tag}

@@ -397,3 +397,39 @@ def test_normwav_in_place_and_batched(eng):
         assert torch.equal(y, z)
         for u, w in enumerate(waves):
             assert np.array_equal(y[u, :lens[u]].cpu().numpy(), orc.norm_wav(w, always)), (always, u)
+
+
+def test_rawboost12_offline_cache_branch(eng, tmp_path, monkeypatch):
+    """``RawBoost12`` with ``online_aug`` off (asvspoof_2019_augall_3.py:365-374): compute once and write ``<aug_dir>/RawBoost12/<utt>``
+    as 16-bit PCM, afterwards load the file instead of computing (no draw is consumed then). soundfile / librosa are absent
+    here exactly as in the survey container, so the two calls the branch makes are served by stand-ins."""
+    import sys
+    import types
+    from conftest import stream_digest
+    from scl_deepfake_audio_detection_b200 import RawBoost as rb
+    store = {}
+    sf = types.ModuleType("soundfile")
+    sf.write = lambda path, wav, sr, subtype=None: store.__setitem__(path, (np.clip(np.round(np.asarray(wav) * 32768.0), -32768, 32767).astype(np.int16), sr, subtype))
+    lr = types.ModuleType("librosa")
+    lr.load = lambda path, sr=None, mono=True: (store[path][0].astype(np.float32) / 32768.0, sr)
+    monkeypatch.setitem(sys.modules, "soundfile", sf)
+    monkeypatch.setitem(sys.modules, "librosa", lr)
+    monkeypatch.setattr("os.path.exists", lambda p, _orig=__import__("os").path.exists: p in store or _orig(p))
+    args = orc.make_args(online_aug=False, aug_dir=str(tmp_path))
+    x = orc.synth_utterance(5, 9000, False)
+    np.random.seed(17)
+    first = rb.RawBoost12(x, args, 16000, audio_path="/corpus/bonafide/LA_T_1.wav")
+    after_first = stream_digest()
+    np.random.seed(17)
+    want = orc.process(x, 16000, ARGS, 5)
+    assert max_err(first, want) <= TOL
+    (path, (pcm, sr, subtype)), = store.items()
+    assert path.endswith("RawBoost12/LA_T_1.wav") and sr == 16000 and subtype == "PCM_16"
+    np.random.seed(17)
+    second = rb.RawBoost12(x, args, 16000, audio_path="/corpus/bonafide/LA_T_1.wav")
+    np.random.seed(17)
+    untouched = stream_digest()
+    assert np.array_equal(second, pcm.astype(np.float32) / 32768.0) and max_err(second, first) <= 1.0 / 32768.0
+    np.random.seed(17)
+    rb.RawBoost12(x, args, 16000, audio_path="/corpus/bonafide/LA_T_1.wav")
+    assert stream_digest() == untouched and after_first != untouched  # the cached call draws nothing
