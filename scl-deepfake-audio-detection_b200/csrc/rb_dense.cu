@@ -15,6 +15,8 @@
 // non-negative floats the unsigned order is the numeric order and every NaN sorts above +inf), so the result is independent
 // of the reduction order, bit-exact against numpy, and NaN propagates like np.amax. DESIGN.md 4.2 has the measurements and the
 // designs this one replaced.
+#include <stdlib.h>
+
 #include "rb_common.cuh"
 #include "rb_dense.cuh"
 #include "rb_finalize.cuh"
@@ -88,6 +90,9 @@ mask_build_global_kernel(const int32_t* __restrict__ isd_off, const int32_t* __r
 #ifndef RB_STREAM_RESCALE_U
 #define RB_STREAM_RESCALE_U 8
 #endif
+#ifndef RB_STREAM_LAG
+#define RB_STREAM_LAG 48
+#endif
 constexpr int kSThreads = RB_STREAM_THREADS;     // threads per CTA
 constexpr int kSU = RB_STREAM_CHUNKS;            // float4 chunks per thread and sub-tile
 constexpr int kSub = RB_STREAM_SUBTILES;         // sub-tiles per tile CTA (two of them in flight at any time)
@@ -133,14 +138,21 @@ struct StreamArgs {
   float g_sd;
   float* out;                // [B][ld]; may equal a when !kSum (in place: the copy is skipped)
   uint2* state;              // [B] {peak bits, tiles arrived}; zero on entry, left zero
+  int B;                     // utterances of this launch
+  int lag;                   // the finisher of utterance u sits behind the tiles of utterance u + lag in the grid
 };
 
 template <bool kIsd, bool kSum>
 __global__ void __launch_bounds__(kSThreads, RB_STREAM_MIN_BLOCKS)
 norm_stream_kernel(const StreamArgs s) {
   __shared__ uint32_t scratch[kSThreads / 32];
+  // Block g * (ntiles + 1) + j: j < ntiles is tile j of utterance g; j == ntiles is the finisher of utterance g - lag. Placing
+  // a finisher `lag` utterances behind its tiles in the dispatch order means it is started when its row is (nearly) complete
+  // instead of spinning -- and holding one of the SM's two CTA slots -- for as long as its tiles take.
   const int per = s.ntiles + 1;
-  const int u = blockIdx.x / per, tile = blockIdx.x - u * per;
+  const int g = blockIdx.x / per, tile = blockIdx.x - g * per;
+  const int u = tile < s.ntiles ? g : g - s.lag;
+  if (u < 0 || u >= s.B) return;
   const int tid = threadIdx.x;
   const int len = min(s.len[u], s.ld);  // (a length beyond the row stride would leave the finisher waiting for tiles that do not exist)
   const float* ra = s.a + (size_t)u * s.ld;
@@ -218,13 +230,19 @@ norm_stream_kernel(const StreamArgs s) {
   // ---- finisher CTA: impulses, exact peak, conditional rescale (all through L2) ---------------------------------------------
   const int nact = (len + kSTile - 1) / kSTile;  // tiles of this utterance that do work
   if (nact <= 0) return;
-  // The impulse values depend on the INPUT only, so the first round of them (all of them for a typical utterance) is
-  // gathered and evaluated before the row is complete; only their stores have to wait for the tiles.
+  // The impulse values depend on the INPUT only. With lag == 0 the finisher starts right behind its row's tiles: the first round
+  // of impulses (all of them for a typical utterance) is gathered from the input row -- in flight or just read -- and evaluated
+  // before the row is complete, and only the stores wait. With a lag the finisher starts when the row is complete, and the
+  // samples are gathered from the OUTPUT row instead (the same values: the tiles copied them): its lines are dirty and stay in
+  // L2, where the clean lines of the input row are the first to be evicted (measured: with the input row as the source a lag
+  // of 64 utterances costs 25 %, see profiles/r02_stream_lag_sweep.log).
   constexpr int kU = RB_STREAM_IMP_U;  // impulses in flight per thread
   const int ibeg = kIsd ? s.isd_off[u] : 0, iend = kIsd ? s.isd_off[u + 1] : 0;
   uint32_t mt = 0u, mx = 0u;  // largest new magnitude / largest magnitude an impulse replaced
   int p0[kU];
   float t0[kU];
+  const bool early = s.lag == 0;
+  const float* gsrc = early ? ra : ro;
   auto impulse_round = [&](int i0, int (&p)[kU], float (&t)[kU]) {
     double fr[kU];
     float xv[kU];
@@ -237,7 +255,7 @@ norm_stream_kernel(const StreamArgs s) {
 #pragma unroll
     for (int k = 0; k < kU; ++k) {
       fr[k] = (p[k] >= 0) ? __ldg(s.isd_fr + i0 + k * kSThreads) : 0.0;
-      xv[k] = (p[k] >= 0) ? __ldcg(ra + p[k]) : 0.f;
+      xv[k] = (p[k] >= 0) ? __ldcg(gsrc + p[k]) : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < kU; ++k) {
@@ -249,7 +267,7 @@ norm_stream_kernel(const StreamArgs s) {
       }
     }
   };
-  if (kIsd) impulse_round(ibeg + tid, p0, t0);
+  if (kIsd && early) impulse_round(ibeg + tid, p0, t0);
   if (tid == 0) {
     uint32_t spins = 0;
     while (ld_relaxed(st_count) < (uint32_t)nact) {
@@ -268,6 +286,7 @@ norm_stream_kernel(const StreamArgs s) {
   uint32_t pk = M;
   const int nchunk = (len + 3) >> 2;
   if (kIsd) {
+    if (!early) impulse_round(ibeg + tid, p0, t0);
 #pragma unroll
     for (int k = 0; k < kU; ++k)
       if (p0[k] >= 0) __stcg(ro + p0[k], t0[k]);
@@ -380,6 +399,21 @@ int launch_mask_build(const int32_t* isd_off, const int32_t* isd_idx, const int3
   return RB_OK;
 }
 
+// Rows between an utterance's tiles and its finisher in the dispatch order (RAWBOOST_B200_STREAM_LAG overrides both defaults,
+// for measurements). Measured on the B200 (profiles/r02_stream_lag_sweep.log, B = 4096): a finisher that starts later does not
+// hold a CTA slot while it waits -- plain normWav goes from 0.388 ms (lag 0) to 0.369 (48) and 0.348 (192), with half the rows
+// rescaled from 0.474 to 0.457 (64) -- but the rows it comes back to leave L2 after ~64-96 utterances (0.60 ms and more beyond),
+// and with impulses any lag loses more than it gains (the early gather from the in-flight input row is what makes them cheap:
+// 0.445 ms at lag 0, 0.51 at 16-64, 0.61 at 192). Hence: impulses -> 0, plain normWav -> 48.
+static int lag_rows(bool isd) {
+  static const int env = [] {
+    const char* e = getenv("RAWBOOST_B200_STREAM_LAG");
+    return e ? (atoi(e) < 0 ? 0 : atoi(e)) : -1;
+  }();
+  if (env >= 0) return env;
+  return isd ? 0 : RB_STREAM_LAG;
+}
+
 int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B, int ld, int always, const int32_t* isd_off,
                        const int32_t* isd_idx, const double* isd_fr, float g_sd, float* out, void* state, cudaStream_t st) {
   if (B <= 0 || ld <= 0) return RB_OK;
@@ -394,7 +428,7 @@ int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B
   s.isd_idx = isd_idx;
   s.isd_fr = isd_fr;
   s.g_sd = g_sd;
-  const int per = max(1, (int)(0x7fffffff / (long long)(s.ntiles + 1)));  // utterances per launch (grid.x < 2^31)
+  const int per = max(1, (int)(0x7fffffff / (long long)(s.ntiles + 1)) - 4096);  // utterances per launch (grid.x < 2^31)
   for (int b0 = 0; b0 < B; b0 += per) {
     const int nb = min(per, B - b0);
     s.a = a + (size_t)b0 * ld;
@@ -403,7 +437,9 @@ int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B
     s.isd_off = isd ? isd_off + b0 : nullptr;
     s.out = out + (size_t)b0 * ld;
     s.state = (uint2*)state + b0;
-    const unsigned grid = (unsigned)nb * (unsigned)(s.ntiles + 1);
+    s.B = nb;
+    s.lag = lag_rows(isd);
+    const unsigned grid = (unsigned)(nb + s.lag) * (unsigned)(s.ntiles + 1);
     if (isd) norm_stream_kernel<true, false><<<grid, kSThreads, 0, st>>>(s);
     else if (b) norm_stream_kernel<false, true><<<grid, kSThreads, 0, st>>>(s);
     else norm_stream_kernel<false, false><<<grid, kSThreads, 0, st>>>(s);
