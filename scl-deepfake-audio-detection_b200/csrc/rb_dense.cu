@@ -151,7 +151,7 @@ norm_stream_kernel(const StreamArgs s) {
   // instead of spinning -- and holding one of the SM's two CTA slots -- for as long as its tiles take.
   const int per = s.ntiles + 1;
   const int g = blockIdx.x / per, tile = blockIdx.x - g * per;
-  const int u = tile < s.ntiles ? g : g - s.lag;
+  const int u = (kIsd || tile < s.ntiles) ? g : g - s.lag;
   if (u < 0 || u >= s.B) return;
   const int tid = threadIdx.x;
   const int len = min(s.len[u], s.ld);  // (a length beyond the row stride would leave the finisher waiting for tiles that do not exist)
@@ -230,19 +230,15 @@ norm_stream_kernel(const StreamArgs s) {
   // ---- finisher CTA: impulses, exact peak, conditional rescale (all through L2) ---------------------------------------------
   const int nact = (len + kSTile - 1) / kSTile;  // tiles of this utterance that do work
   if (nact <= 0) return;
-  // The impulse values depend on the INPUT only. With lag == 0 the finisher starts right behind its row's tiles: the first round
-  // of impulses (all of them for a typical utterance) is gathered from the input row -- in flight or just read -- and evaluated
-  // before the row is complete, and only the stores wait. With a lag the finisher starts when the row is complete, and the
-  // samples are gathered from the OUTPUT row instead (the same values: the tiles copied them): its lines are dirty and stay in
-  // L2, where the clean lines of the input row are the first to be evicted (measured: with the input row as the source a lag
-  // of 64 utterances costs 25 %, see profiles/r02_stream_lag_sweep.log).
+  // The impulse values depend on the INPUT only, so the first round of them (all of them for a typical utterance) is
+  // gathered -- from the input row, which the utterance's tiles are pulling through L2 at this very moment -- and evaluated
+  // before the row is complete; only their stores have to wait for the tiles. (This is why a finisher with impulses sits
+  // right behind its tiles, lag 0: started later it would find neither row in L2, see lag_rows() below.)
   constexpr int kU = RB_STREAM_IMP_U;  // impulses in flight per thread
   const int ibeg = kIsd ? s.isd_off[u] : 0, iend = kIsd ? s.isd_off[u + 1] : 0;
   uint32_t mt = 0u, mx = 0u;  // largest new magnitude / largest magnitude an impulse replaced
   int p0[kU];
   float t0[kU];
-  const bool early = s.lag == 0;
-  const float* gsrc = early ? ra : ro;
   auto impulse_round = [&](int i0, int (&p)[kU], float (&t)[kU]) {
     double fr[kU];
     float xv[kU];
@@ -255,7 +251,7 @@ norm_stream_kernel(const StreamArgs s) {
 #pragma unroll
     for (int k = 0; k < kU; ++k) {
       fr[k] = (p[k] >= 0) ? __ldg(s.isd_fr + i0 + k * kSThreads) : 0.0;
-      xv[k] = (p[k] >= 0) ? __ldcg(gsrc + p[k]) : 0.f;
+      xv[k] = (p[k] >= 0) ? __ldcg(ra + p[k]) : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < kU; ++k) {
@@ -267,7 +263,7 @@ norm_stream_kernel(const StreamArgs s) {
       }
     }
   };
-  if (kIsd && early) impulse_round(ibeg + tid, p0, t0);
+  if (kIsd) impulse_round(ibeg + tid, p0, t0);
   if (tid == 0) {
     uint32_t spins = 0;
     while (ld_relaxed(st_count) < (uint32_t)nact) {
@@ -286,7 +282,6 @@ norm_stream_kernel(const StreamArgs s) {
   uint32_t pk = M;
   const int nchunk = (len + 3) >> 2;
   if (kIsd) {
-    if (!early) impulse_round(ibeg + tid, p0, t0);
 #pragma unroll
     for (int k = 0; k < kU; ++k)
       if (p0[k] >= 0) __stcg(ro + p0[k], t0[k]);
@@ -404,14 +399,15 @@ int launch_mask_build(const int32_t* isd_off, const int32_t* isd_idx, const int3
 // hold a CTA slot while it waits -- plain normWav goes from 0.388 ms (lag 0) to 0.369 (48) and 0.348 (192), with half the rows
 // rescaled from 0.474 to 0.457 (64) -- but the rows it comes back to leave L2 after ~64-96 utterances (0.60 ms and more beyond),
 // and with impulses any lag loses more than it gains (the early gather from the in-flight input row is what makes them cheap:
-// 0.445 ms at lag 0, 0.51 at 16-64, 0.61 at 192). Hence: impulses -> 0, plain normWav -> 48.
+// 0.445 ms at lag 0, 0.51 at 16-64, 0.61 at 192, whether the late gather reads the input or the output row). Hence:
+// impulses -> 0 (compiled in), plain normWav -> 48.
 static int lag_rows(bool isd) {
   static const int env = [] {
     const char* e = getenv("RAWBOOST_B200_STREAM_LAG");
     return e ? (atoi(e) < 0 ? 0 : atoi(e)) : -1;
   }();
-  if (env >= 0) return env;
-  return isd ? 0 : RB_STREAM_LAG;
+  if (isd) return 0;  // (the sweep with impulses was taken with a build whose finisher could gather late)
+  return env >= 0 ? env : RB_STREAM_LAG;
 }
 
 int launch_norm_stream(const float* a, const float* b, const int32_t* len, int B, int ld, int always, const int32_t* isd_off,
