@@ -757,7 +757,7 @@ def bench_config4(eng, args, items=8192, steps=3, length=64600, trim=64000, orc=
     [V, 64000] with the label vector. Plans are drawn on the device from the seeds, overlapped with the filtering; the
     assembly reads x / y in place. ``orc``: the oracle module for an in-run parity sample (checker only)."""
     import torch
-    from scl_deepfake_audio_detection_b200 import multiview, plans as _plans, workload
+    from scl_deepfake_audio_detection_b200 import plans as _plans, workload
     from scl_deepfake_audio_detection_b200.multiview import LAYOUT_MODEL, assemble_ex, item_labels, item_view_rows
     G, nvoc = int(items), 3
     B, V = 4 * G, 8

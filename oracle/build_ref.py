@@ -18,7 +18,6 @@ import importlib.util
 import marshal
 import os
 import py_compile
-import sys
 import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -71,17 +71,19 @@ def _as_wave(x):
 
 
 def _run_single(algo, x, plan):
-    """One utterance through ``rb_process``: returns a new float32 array of x's length. ``plan``: an ``UtterancePlan`` or an
+    """One utterance through the host-buffer entry (``rb_process_host``: ONE C call copies the waveform and the plan in, runs
+    the kernels and copies the result out): returns a new float32 array of x's length. ``plan``: an ``UtterancePlan`` or an
     already packed one-utterance ``BatchPlan``."""
     eng = default_engine(_DEVICE)
     n = x.shape[0]
     if n == 0:
         return np.zeros(0, dtype=np.float32)
-    xd, ld = eng.pack_waveforms([x])
     bp = plan if isinstance(plan, _plans.BatchPlan) else (_plans.pack([plan]) if plan is not None else None)
-    dp = eng.upload_plan(bp) if bp is not None else None
-    y = eng.process(algo, xd, ld, dp)
-    return y[0, :n].cpu().numpy()
+    ld = bp.ld if bp is not None else _plans.padded_ld(n)
+    xh = np.zeros((1, ld), dtype=np.float32)
+    xh[0, :n] = x  # (float64 input is rounded to float32 here, see the module docstring)
+    y = eng.process_host(algo, xh, bp)
+    return y[0, :n].copy()
 
 
 def normWav(x, always):

@@ -16,7 +16,7 @@ Integer work (crop start, index map) is bit-exact; the samples are copies of the
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -11,7 +11,7 @@ A :class:`BatchPlan` packs the per-utterance draws of a batch into the CSR array
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
 import numpy as np

@@ -15,7 +15,7 @@ def bench(fn, n):
 for planner in ("native", "numpy"):
     rb._PLANNER = planner
     np.random.seed(1)
-    for algo in (5, 2, 3):
+    for algo in (5, 2, 3, 3, 2, 5):
         ms = bench(lambda: rb.process_Rawboost_feature(x, 16000, args, algo), 30)
         print(f"B200 drop-in, draws by {planner:6s} algo {algo}: {ms:7.3f} ms / utterance  ({1e3/ms:7.1f} utt/s per caller)")
 np.random.seed(1)
