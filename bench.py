@@ -507,6 +507,12 @@ def gpu_arm(a):
         v, ms, n = run_cpu_arm(algo, L, a.cpu_per_core, b.cores, 2, 1)
         cpu = {"value": v, "unit": UNIT, "cores": b.cores, "kind": kind,
                "sample": cpu_description(kind, n, a.cpu_per_core, b.cores, ", 2 timed steps")}
+        if configs:  # BASELINE config 1: algo 1 on 32 utterances through the reference's CPU path (one batch, all host cores)
+            per_core = max(1, 32 // b.cores)
+            v1, ms1, n1 = run_cpu_arm(1, L, per_core, min(b.cores, 32), 2, 1)
+            configs["config1_algo1_cpu_b32"] = {"algo": 1, "value": v1, "unit": UNIT, "ms_per_step": ms1, "utterances_per_step": n1,
+                                                "kind": kind, "cores": min(b.cores, 32),
+                                                "what": "the reference CPU path itself (no GPU): the configuration BASELINE.json lists first"}
 
     if rank == 0:
         line = {
