@@ -288,3 +288,43 @@ def test_oracle_dataset_item_matches_reference(golden2):
         assert np.max(np.abs(data.astype(np.float64) - arrays[f"getitem{idx}_data"])) <= 1e-6
         assert np.array_equal(label, arrays[f"getitem{idx}_label"])
         assert stream_digest() == m["stream"]
+
+
+def test_compiled_reference_matches_the_oracle():
+    """``oracle/_ref`` (the reference's own bytecode, oracle/build_ref.py) and the numpy restatement agree bit for bit on every
+    algo, and consume the global stream identically -- the CPU arm of the bench times the former, the tests check with the latter."""
+    from oracle import build_ref
+    if not build_ref.available():
+        build_ref.build()  # possible only where /root/reference exists
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip(f"oracle/_ref not usable here: {build_ref.last_error}")
+    ops, dispatch = ref
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for algo in range(0, 9):
+            for loud in (False, True):
+                x = orc.synth_utterance(3, 8000, loud)
+                np.random.seed(77)
+                a = dispatch(x, 16000, ARGS, algo)
+                sa = stream_digest()
+                np.random.seed(77)
+                b = orc.process(x, 16000, ARGS, algo)
+                assert stream_digest() == sa, algo
+                assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b), algo
+        x = orc.synth_utterance(4, 5000, True)
+        assert np.array_equal(ops.normWav(x * 3, 0), orc.norm_wav(x * 3, 0))
+
+
+def test_item_view_rows_and_labels_follow_the_dataset_order():
+    """Row table / label vector of the in-place assembly == the view order and labels of Dataset_for.__getitem__
+    (asvspoof_2019_augall_3.py:133, 143-146): anchor, augmented anchor, additional bona fide, vocoded, augmented vocoded."""
+    from scl_deepfake_audio_detection_b200 import multiview
+    rows = multiview.item_view_rows(2, 3, [[8, 9], [10, 11]])
+    # per item the inputs sit as [voc0, voc1, voc2, anchor]; negative = the RawBoost result of that row
+    assert rows.tolist() == [[3, -4, 8, 9, 0, 1, 2, -1, -2, -3], [7, -8, 10, 11, 4, 5, 6, -5, -6, -7]]
+    assert multiview.item_view_rows(1, 3).tolist() == [[3, -4, 0, 1, 2, -1, -2, -3]]
+    assert multiview.item_labels(3, 2).tolist() == [1, 1, 1, 1, 0, 0, 0, 0, 0, 0]
+    _, _, label = orc.dataset_item(0, orc.CORPUS_IDS, orc.corpus_wave, orc.make_args(), orc.CORPUS_VOCODERS, 2, 4000)
+    assert label.tolist() == multiview.item_labels(3, 2).tolist()
