@@ -39,12 +39,46 @@ namespace rb {
 
 namespace {
 
+// Tile geometry as a function of KR, the consecutive outputs per thread. The bank and the SSI kernel use rb_common.cuh's kR
+// (20: 40 accumulator + 24 window registers leave room for the tails at four CTAs per SM); the plain single filter
+// (TAIL_NONE: rb_filter_fir, the reverb view) has no tail to carry and runs with 28 outputs per thread -- more FFMA2 per window
+// and tap LDS, fewer tiles per utterance: +3..5 % from K = 131 to K = 1001 (profiles/r02k_fir_single_filter_kr28.log).
+// Strides of 80 B (20) and 112 B (28) both keep the window LDS.128 bank-conflict-free.
+template <int KR>
+struct Geo {
+  static constexpr int kR = KR;
+  static constexpr int kTile = kThreads * KR;
+  static constexpr int kWarpSpan = 32 * KR;
+  static constexpr int kWin = KR + 4;
+  static constexpr int kBodyTaps = kWin;
+  static constexpr int kTapCap = (3 + kSegTaps + 1 + kBodyTaps - 1) / kBodyTaps * kBodyTaps;
+  static constexpr int kXS = kTile + 2 * kHalo + 64;
+  static constexpr int kMaxReach = kXS - (kThreads - 1) * KR - kWin - kBodyTaps;
+  static_assert(KR % 4 == 0 && (KR * 4) % 32 == 16, "window stride must be an odd multiple of 16 B (conflict-free LDS.128)");
+};
+static_assert(Geo<kR>::kXS == kXS && Geo<kR>::kMaxReach == kMaxReach && Geo<kR>::kTapCap == kTapCap, "Geo<kR> is rb_common.cuh's tiling");
+// the names of rb_common.cuh, rebound to the geometry of the instantiation at hand
+#define RB_GEO(KR)                                                     \
+  [[maybe_unused]] constexpr int kR = Geo<KR>::kR;                     \
+  [[maybe_unused]] constexpr int kTile = Geo<KR>::kTile;               \
+  [[maybe_unused]] constexpr int kWarpSpan = Geo<KR>::kWarpSpan;       \
+  [[maybe_unused]] constexpr int kWin = Geo<KR>::kWin;                 \
+  [[maybe_unused]] constexpr int kBodyTaps = Geo<KR>::kBodyTaps;       \
+  [[maybe_unused]] constexpr int kTapCap = Geo<KR>::kTapCap;           \
+  [[maybe_unused]] constexpr int kXS = Geo<KR>::kXS;                   \
+  [[maybe_unused]] constexpr int kMaxReach = Geo<KR>::kMaxReach
+
+#ifndef RB_KR_ONE
+#define RB_KR_ONE 28
+#endif
+
+template <int KR>
 struct __align__(16) FirSmem {
-  float x1[kXS];        // staged samples, x1[j] = x[gbase + j]
-  float xp[kXS];        // x1 ** power of the current filter (also reused to transpose the outputs)
-  float he[kTapCap];    // reversed, zero-padded taps for even outputs
-  float ho[kTapCap];    // the same shifted by one for odd outputs
-  float red[4][kStatN]; // per-warp partial statistics
+  float x1[Geo<KR>::kXS];      // staged samples, x1[j] = x[gbase + j]
+  float xp[Geo<KR>::kXS];      // x1 ** power of the current filter (also reused to transpose the outputs)
+  float he[Geo<KR>::kTapCap];  // reversed, zero-padded taps for even outputs
+  float ho[Geo<KR>::kTapCap];  // the same shifted by one for odd outputs
+  float red[4][kStatN];        // per-warp partial statistics
 };
 
 __device__ __forceinline__ float pow_round_once(float v, int p) {
@@ -62,8 +96,9 @@ __device__ __forceinline__ float pow_round_once(float v, int p) {
 
 // xp[j] = x1[j] ** kPow over the whole staged range, four samples per step (LDS.128 / STS.128, the multiply chain unrolled).
 // Same arithmetic as pow_round_once: fp64 products in the same order, rounded to fp32 once.
-template <int kPow>
+template <int kPow, int KR>
 __device__ __forceinline__ void stage_power(float* __restrict__ xp, const float* __restrict__ x1) {
+  RB_GEO(KR);
   static_assert(kXS % 4 == 0, "staged range must be whole float4 chunks");
 #ifdef RB_POW_FP32
   for (int j = threadIdx.x; j < kXS; j += kThreads) xp[j] = pow_round_once(x1[j], kPow);
@@ -85,7 +120,9 @@ __device__ __forceinline__ void stage_power(float* __restrict__ xp, const float*
 }
 
 // Stage x[gbase .. gbase+kXS) of one utterance row into smem, zero outside [0, len).
+template <int KR>
 __device__ __forceinline__ void stage_x(float* __restrict__ dst, const float* __restrict__ row, int len, int gbase) {
+  RB_GEO(KR);
   // gbase is a multiple of 4 and the row is 16-byte aligned, so every chunk is an aligned float4.
   for (int c = threadIdx.x; c < kXS / 4; c += kThreads) {
     const int pos = gbase + 4 * c;
@@ -108,9 +145,10 @@ __device__ __forceinline__ void stage_x(float* __restrict__ dst, const float* __
 // bank, +4.4 % / +2.7 % on the single short SSI filter).
 // ngroups = number of 4-tap groups that hold non-zero taps: full 24-tap bodies first, then a partial last body that stops
 // after its last useful group (uniform branch), so zero padding costs at most 3 taps + alignment instead of up to 23.
-template <int kUnroll>
-__device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __restrict__ src, const float* __restrict__ he,
+template <int kUnroll, int KR>
+__device__ __forceinline__ void conv_segment(float2 (&acc)[KR], const float* __restrict__ src, const float* __restrict__ he,
                                              const float* __restrict__ ho, int e0, int ngroups) {
+  RB_GEO(KR);
   float2 w[kWin / 2];
 #ifdef RB_WIN_LDS64
   // Window loads as 64-bit pairs: leaves ptxas free to keep every window pair in the register bank class the
@@ -203,6 +241,9 @@ __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __r
 #ifndef RB_UNROLL_LNL
 #define RB_UNROLL_LNL 4
 #endif
+#ifndef RB_UNROLL_ONE
+#define RB_UNROLL_ONE 2
+#endif
 #ifndef RB_MIN_BLOCKS
 #define RB_MIN_BLOCKS 4
 #endif
@@ -211,12 +252,13 @@ __device__ __forceinline__ void conv_segment(float2 (&acc)[kR], const float* __r
 #endif
 // kTailMode is a compile-time constant: each tail (none / LnL[->ISD] / SSI) is its own kernel, so the code of one never weighs on
 // the register allocation and instruction schedule of another.
-template <int kTailMode>
+template <int kTailMode, int KR>
 __global__ void __launch_bounds__(kThreads, kTailMode == TAIL_SSI ? RB_MIN_BLOCKS_SSI : RB_MIN_BLOCKS)
 fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr, int ld, const float* __restrict__ taps,
                 const int32_t* __restrict__ tap_off, int n_f, int pow_base, int pow_step, float* __restrict__ y,
                 float* __restrict__ stats, const uint32_t* __restrict__ mask, int mask_ld, FirTail tail) {
-  __shared__ FirSmem sm;
+  RB_GEO(KR);
+  __shared__ FirSmem<KR> sm;
   __shared__ int s_last;
   const int u = blockIdx.y;
   const int tile = blockIdx.x;
@@ -244,6 +286,26 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
   // overlap instead of following each other (it matters for single short filters: ~1 us of ~5 us of fixed cost per tile).
   // staged0: the first segment's taps are already in he / ho when the filter loop gets there.
   bool staged0 = false;
+  // SSI: the signal tile is only needed for its sum of squares. Its loads go out with the start-up round trip as well and are
+  // reduced to one register right behind the staging, instead of costing every tile a third, exposed round trip in the epilogue.
+  float aux_sq = 0.f;
+  float4 av[kTailMode == TAIL_SSI ? kR / 4 : 1];
+  if (kTailMode == TAIL_SSI) {
+    const float* arow = tail.aux + (size_t)u * ld + tile0;
+    const int valid = min(kTile, len - tile0);
+#pragma unroll
+    for (int k = 0; k < kR / 4; ++k) {
+      const int p = 4 * (k * kThreads + tid);
+      if (p + 3 < valid) {
+        av[k] = __ldg(reinterpret_cast<const float4*>(arow + p));
+      } else {
+        av[k].x = (p + 0 < valid) ? __ldg(arow + p + 0) : 0.f;
+        av[k].y = (p + 1 < valid) ? __ldg(arow + p + 1) : 0.f;
+        av[k].z = (p + 2 < valid) ? __ldg(arow + p + 2) : 0.f;
+        av[k].w = (p + 3 < valid) ? __ldg(arow + p + 3) : 0.f;
+      }
+    }
+  }
   {
     const int t0 = tap_off[u * n_f];
     const int K = tap_off[u * n_f + 1] - t0;
@@ -260,7 +322,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
         const int i = tid + q * kThreads, m = i - z;
         tp[q] = (i < nbody * kBodyTaps && m >= 0 && m < kseg) ? __ldg(taps + t0 + (K - 1 - m)) : 0.f;
       }
-      stage_x(sm.x1, row, len, gbase);
+      stage_x<KR>(sm.x1, row, len, gbase);
 #pragma unroll
       for (int q = 0; q < kPre; ++q) {
         const int i = tid + q * kThreads;
@@ -272,7 +334,17 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       }
       staged0 = true;
     } else {
-      stage_x(sm.x1, row, len, gbase);
+      stage_x<KR>(sm.x1, row, len, gbase);
+    }
+  }
+
+  if (kTailMode == TAIL_SSI) {
+#pragma unroll
+    for (int k = 0; k < kR / 4; ++k) {
+      aux_sq = fmaf(av[k].x, av[k].x, aux_sq);
+      aux_sq = fmaf(av[k].y, av[k].y, aux_sq);
+      aux_sq = fmaf(av[k].z, av[k].z, aux_sq);
+      aux_sq = fmaf(av[k].w, av[k].w, aux_sq);
     }
   }
 
@@ -298,7 +370,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       if (e < 0 || e + kseg > kMaxReach) {  // uniform: restage the samples around this segment
         gbase = (tile0 + d) & ~3;
         e = tile0 + d - gbase;
-        stage_x(sm.x1, row, len, gbase);
+        stage_x<KR>(sm.x1, row, len, gbase);
         staged_pow = 1;
         __syncthreads();
       }
@@ -318,10 +390,10 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       if (power != 1) {
         if (staged_pow != power) {
           switch (power) {  // uniform; the LnL bank uses 2..N_f
-            case 2: stage_power<2>(sm.xp, sm.x1); break;
-            case 3: stage_power<3>(sm.xp, sm.x1); break;
-            case 4: stage_power<4>(sm.xp, sm.x1); break;
-            case 5: stage_power<5>(sm.xp, sm.x1); break;
+            case 2: stage_power<2, KR>(sm.xp, sm.x1); break;
+            case 3: stage_power<3, KR>(sm.xp, sm.x1); break;
+            case 4: stage_power<4, KR>(sm.xp, sm.x1); break;
+            case 5: stage_power<5, KR>(sm.xp, sm.x1); break;
             default:
               for (int j = tid; j < kXS; j += kThreads) sm.xp[j] = pow_round_once(sm.x1[j], power);
           }
@@ -330,7 +402,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
         src = sm.xp;
       }
       __syncthreads();
-      if (warp_active) conv_segment<kTailMode == TAIL_AFFINE ? RB_UNROLL_LNL : 2>(acc, src, sm.he, sm.ho, e - z, ngroups);
+      if (warp_active) conv_segment<kTailMode == TAIL_AFFINE ? RB_UNROLL_LNL : RB_UNROLL_ONE, KR>(acc, src, sm.he, sm.ho, e - z, ngroups);
     }
   }
   __syncthreads();  // everyone is done reading xp; reuse it to transpose the outputs
@@ -373,6 +445,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
     s_max = warp_max(s_max);
     s_minu = warp_min(s_minu);
     s_maxu = warp_max(s_maxu);
+    if (kTailMode == TAIL_SSI) aux_sq = warp_sum(aux_sq);
     if (lane == 0) {
       sm.red[warp][S_SUM] = s_sum;
       sm.red[warp][S_SUMSQ] = s_sq;
@@ -380,12 +453,13 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       sm.red[warp][S_MAX] = s_max;
       sm.red[warp][S_MINU] = s_minu;
       sm.red[warp][S_MAXU] = s_maxu;
+      if (kTailMode == TAIL_SSI) sm.red[warp][S_AUXSQ] = aux_sq;
     }
   }
   __syncthreads();
   if (stats && tid < kStatN) {
     float v;
-    if (tid == S_SUM || tid == S_SUMSQ) v = (sm.red[0][tid] + sm.red[1][tid]) + (sm.red[2][tid] + sm.red[3][tid]);
+    if (tid == S_SUM || tid == S_SUMSQ || (kTailMode == TAIL_SSI && tid == S_AUXSQ)) v = (sm.red[0][tid] + sm.red[1][tid]) + (sm.red[2][tid] + sm.red[3][tid]);
     else if (tid == S_MIN || tid == S_MINU) v = fminf(fminf(sm.red[0][tid], sm.red[1][tid]), fminf(sm.red[2][tid], sm.red[3][tid]));
     else if (tid == S_MAX || tid == S_MAXU) v = fmaxf(fmaxf(sm.red[0][tid], sm.red[1][tid]), fmaxf(sm.red[2][tid], sm.red[3][tid]));
     else v = 0.f;
@@ -409,32 +483,6 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
   // ---- fused tail: the CTA that finishes the last tile of an utterance finalises the whole utterance -----------------------
   // (per-utterance reductions need every tile, so this is the one grid-level dependency of the path; the raw tiles were
   // written a moment ago and are read back from L2 while the other CTAs of the SM keep the FP32 pipe busy.)
-  if (kTailMode == TAIL_SSI) {  // per-tile sum of squares of the signal the noise is added to
-    const float* arow = tail.aux + (size_t)u * ld + tile0;
-    float sq = 0.f;
-#pragma unroll
-    for (int k = 0; k < kR / 4; ++k) {
-      const int p = 4 * (k * kThreads + tid);
-      if (p + 3 < valid) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(arow + p));
-        sq = fmaf(v.x, v.x, sq);
-        sq = fmaf(v.y, v.y, sq);
-        sq = fmaf(v.z, v.z, sq);
-        sq = fmaf(v.w, v.w, sq);
-      } else {
-        for (int q = 0; q < 4; ++q)
-          if (p + q < valid) {
-            const float e = __ldg(arow + p + q);
-            sq = fmaf(e, e, sq);
-          }
-      }
-    }
-    sq = warp_sum(sq);
-    __syncthreads();  // sm.red was read by the statistics above
-    if (lane == 0) sm.red[warp][0] = sq;
-    __syncthreads();
-    if (tid == 0) st_out[S_AUXSQ] = (sm.red[0][0] + sm.red[1][0]) + (sm.red[2][0] + sm.red[3][0]);
-  }
   const int nact = (len + kTile - 1) / kTile;  // tiles of this utterance that do work (the others returned at once)
   __threadfence();
   __syncthreads();
@@ -563,14 +611,15 @@ int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const flo
     RB_CUDA(cudaMemsetAsync(tail.counters, 0, (size_t)B * sizeof(uint32_t), st));
   }
   // gridDim.y is limited to 65535: split very large batches over several launches.
-  const int ntiles = tiles_for(ld);
+  // tiles of the instantiation launched; the statistics (tails only) are laid out [B][tiles_for(ld)][kStatN]
+  const int ntiles = tail.mode == TAIL_NONE ? (ld + Geo<RB_KR_ONE>::kTile - 1) / Geo<RB_KR_ONE>::kTile : tiles_for(ld);
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = min(65535, B - b0);
     dim3 grid(ntiles, nb);
     profile_begin(st);
-    auto kernel = tail.mode == TAIL_AFFINE ? fir_bank_kernel<TAIL_AFFINE>
-                  : tail.mode == TAIL_SSI  ? fir_bank_kernel<TAIL_SSI>
-                                           : fir_bank_kernel<TAIL_NONE>;
+    auto kernel = tail.mode == TAIL_AFFINE ? fir_bank_kernel<TAIL_AFFINE, kR>
+                  : tail.mode == TAIL_SSI  ? fir_bank_kernel<TAIL_SSI, kR>
+                                           : fir_bank_kernel<TAIL_NONE, RB_KR_ONE>;
     // Largest shared-memory carve-out: the kernel itself needs little L1, and the device planner's kernels (up to ~100 KB of
     // shared memory per CTA) can then run in what the four FIR CTAs of an SM leave free instead of waiting for them.
     RB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

@@ -363,17 +363,21 @@ def test_fir_kernel_sass_contract():
     import sass_loop_stats
     loops = {}
     for name, ins in sass_loop_stats.functions(_lib.LIB_PATH):
-        m = re.search(r"fir_bank_kernelILi(\d)E", name)
+        m = re.search(r"fir_bank_kernelILi(\d)ELi(\d+)E", name)
         if not m:
             continue
         text = [t for _, t, _ in ins]
         assert not any("STL" in t or "LDL" in t for t in text), "local-memory spills in " + name
         body = [t for _, t, _ in (sass_loop_stats.body_loop(ins) or [])]
-        loops[int(m.group(1))] = (sum("FFMA2" in t for t in body), sum("LDS.128" in t for t in body), len(body))
+        loops[int(m.group(1))] = (int(m.group(2)), sum("FFMA2" in t for t in body), sum("LDS.128" in t for t in body), len(body))
     assert set(loops) == {0, 1, 2}, "one instantiation per tail mode"
-    for mode, (ffma2, lds, total) in loops.items():
-        # a 24-tap body is 240 FFMA2 + 18 LDS.128; the loop holds two (single filters) or four (LnL bank) of them
-        assert ffma2 in (480, 960) and lds == 18 * ffma2 // 240, f"tail mode {mode}: body loop changed shape ({ffma2} FFMA2, {lds} LDS.128)"
+    assert loops[0][0] == 28 and loops[1][0] == loops[2][0] == 20, "outputs per thread: 28 for the plain filter, 20 with a tail"
+    for mode, (kr, ffma2, lds, total) in loops.items():
+        # a body covers kr + 4 taps: (kr + 4) / 4 groups of 2 * kr FFMA2 and 3 LDS.128 (240 + 18 at kr = 20, 448 + 24 at 28);
+        # the loop holds two bodies (single filters) or four (LnL bank)
+        per_body, lds_body = (kr + 4) // 4 * 2 * kr, (kr + 4) // 4 * 3
+        assert ffma2 in (2 * per_body, 4 * per_body) and lds == lds_body * ffma2 // per_body, \
+            f"tail mode {mode}: body loop changed shape ({ffma2} FFMA2, {lds} LDS.128)"
         assert total - ffma2 - lds <= 8, f"tail mode {mode}: {total - ffma2 - lds} other instructions inside the body loop"
     log = os.path.join(os.path.dirname(_lib.LIB_PATH), "librawboost_b200.rb_fir_bank.ptxas.log")
     if os.path.exists(log):
