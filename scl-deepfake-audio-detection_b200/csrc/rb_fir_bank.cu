@@ -68,6 +68,15 @@ static_assert(Geo<kR>::kXS == kXS && Geo<kR>::kMaxReach == kMaxReach && Geo<kR>:
   [[maybe_unused]] constexpr int kXS = Geo<KR>::kXS;                   \
   [[maybe_unused]] constexpr int kMaxReach = Geo<KR>::kMaxReach
 
+#ifndef RB_STAGE_INLINE
+#define RB_STAGE_INLINE __forceinline__
+#endif
+#ifndef RB_STAGE_BATCHED
+#define RB_STAGE_BATCHED(mode) ((mode) != TAIL_AFFINE)
+#endif
+#ifndef RB_KR_SSI
+#define RB_KR_SSI RB_KR
+#endif
 #ifndef RB_KR_ONE
 #define RB_KR_ONE 28
 #endif
@@ -119,11 +128,41 @@ __device__ __forceinline__ void stage_power(float* __restrict__ xp, const float*
 #endif
 }
 
-// Stage x[gbase .. gbase+kXS) of one utterance row into smem, zero outside [0, len).
+// Interior tile (all but the first and the last one or two of an utterance): every load of the thread is issued before the
+// first store, ONE global round trip for the staging instead of one per chunk (the rolled loop of stage_x waits for each
+// LDG.128 before its STS.128: seven / nine serialised round trips at 20 / 28 outputs per thread). Used by the single-filter
+// kernels, whose tiles live 5-15 us (SSI +3.6 %, plain K = 51 +27 %, K = 131 +2.6 %); the bank keeps the rolled loop: its
+// tiles live ~60 us and the extra registers cost its FFMA2 schedule 0.5 % (profiles/r02l_fir_batched_staging.log; a
+// non-inlined copy and batching the edge tiles as well were measured too and are not better).
 template <int KR>
+__device__ RB_STAGE_INLINE void stage_x_interior(float* __restrict__ dst, const float* __restrict__ src_f) {
+  RB_GEO(KR);
+  constexpr int kIter = (kXS / 4 + kThreads - 1) / kThreads;
+  const float4* src = reinterpret_cast<const float4*>(src_f);
+  float4 v[kIter];
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const int c = threadIdx.x + i * kThreads;  // the last, partial round re-reads the final chunk instead of branching
+    v[i] = __ldg(src + ((i + 1) * kThreads <= kXS / 4 ? c : min(c, kXS / 4 - 1)));
+  }
+#pragma unroll
+  for (int i = 0; i < kIter; ++i) {
+    const int c = threadIdx.x + i * kThreads;
+    if ((i + 1) * kThreads <= kXS / 4 || c < kXS / 4) reinterpret_cast<float4*>(dst)[c] = v[i];
+  }
+}
+
+// Stage x[gbase .. gbase+kXS) of one utterance row into smem, zero outside [0, len).
+template <int KR, bool kBatched>
 __device__ __forceinline__ void stage_x(float* __restrict__ dst, const float* __restrict__ row, int len, int gbase) {
   RB_GEO(KR);
   // gbase is a multiple of 4 and the row is 16-byte aligned, so every chunk is an aligned float4.
+#ifndef RB_STAGE_ROLLED
+  if (kBatched && gbase >= 0 && gbase + kXS <= len) {
+    stage_x_interior<KR>(dst, row + gbase);
+    return;
+  }
+#endif
   for (int c = threadIdx.x; c < kXS / 4; c += kThreads) {
     const int pos = gbase + 4 * c;
     float4 v;
@@ -258,6 +297,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
                 const int32_t* __restrict__ tap_off, int n_f, int pow_base, int pow_step, float* __restrict__ y,
                 float* __restrict__ stats, const uint32_t* __restrict__ mask, int mask_ld, FirTail tail) {
   RB_GEO(KR);
+  constexpr bool kBatchedStaging = RB_STAGE_BATCHED(kTailMode);
   __shared__ FirSmem<KR> sm;
   __shared__ int s_last;
   const int u = blockIdx.y;
@@ -322,7 +362,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
         const int i = tid + q * kThreads, m = i - z;
         tp[q] = (i < nbody * kBodyTaps && m >= 0 && m < kseg) ? __ldg(taps + t0 + (K - 1 - m)) : 0.f;
       }
-      stage_x<KR>(sm.x1, row, len, gbase);
+      stage_x<KR, kBatchedStaging>(sm.x1, row, len, gbase);
 #pragma unroll
       for (int q = 0; q < kPre; ++q) {
         const int i = tid + q * kThreads;
@@ -334,7 +374,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       }
       staged0 = true;
     } else {
-      stage_x<KR>(sm.x1, row, len, gbase);
+      stage_x<KR, kBatchedStaging>(sm.x1, row, len, gbase);
     }
   }
 
@@ -370,7 +410,7 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       if (e < 0 || e + kseg > kMaxReach) {  // uniform: restage the samples around this segment
         gbase = (tile0 + d) & ~3;
         e = tile0 + d - gbase;
-        stage_x<KR>(sm.x1, row, len, gbase);
+        stage_x<KR, kBatchedStaging>(sm.x1, row, len, gbase);
         staged_pow = 1;
         __syncthreads();
       }
@@ -423,29 +463,32 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
   for (int r = 0; r < kR; ++r) {
     const float v = acc[r].x + acc[r].y;
     outv[r] = v;
-    if (n0 + r < len) {
-      s_sum += v;
-      s_sq = fmaf(v, v, s_sq);
-      s_min = fminf(s_min, v);
-      s_max = fmaxf(s_max, v);
-      if (!((hit >> r) & 1u)) {
-        s_minu = fminf(s_minu, v);
-        s_maxu = fmaxf(s_maxu, v);
+    if (kTailMode == TAIL_AFFINE) {
+      if (n0 + r < len) {
+        s_sum += v;
+        s_sq = fmaf(v, v, s_sq);
+        s_min = fminf(s_min, v);
+        s_max = fmaxf(s_max, v);
+        if (!((hit >> r) & 1u)) {
+          s_minu = fminf(s_minu, v);
+          s_maxu = fmaxf(s_maxu, v);
+        }
       }
+    } else if (kTailMode == TAIL_SSI) {  // the SSI gain needs the two sums of squares only (rb_finalize.cuh: ssi_scale_block)
+      if (n0 + r < len) s_sq = fmaf(v, v, s_sq);
     }
   }
 #pragma unroll
   for (int m = 0; m < kR / 4; ++m)
     reinterpret_cast<float4*>(sm.xp + tid * kR)[m] = make_float4(outv[4 * m], outv[4 * m + 1], outv[4 * m + 2], outv[4 * m + 3]);
 
-  if (stats) {
+  if (kTailMode == TAIL_AFFINE) {
     s_sum = warp_sum(s_sum);
     s_sq = warp_sum(s_sq);
     s_min = warp_min(s_min);
     s_max = warp_max(s_max);
     s_minu = warp_min(s_minu);
     s_maxu = warp_max(s_maxu);
-    if (kTailMode == TAIL_SSI) aux_sq = warp_sum(aux_sq);
     if (lane == 0) {
       sm.red[warp][S_SUM] = s_sum;
       sm.red[warp][S_SUMSQ] = s_sq;
@@ -453,17 +496,27 @@ fir_bank_kernel(const float* __restrict__ x, const int32_t* __restrict__ len_arr
       sm.red[warp][S_MAX] = s_max;
       sm.red[warp][S_MINU] = s_minu;
       sm.red[warp][S_MAXU] = s_maxu;
-      if (kTailMode == TAIL_SSI) sm.red[warp][S_AUXSQ] = aux_sq;
+    }
+  } else if (kTailMode == TAIL_SSI) {
+    s_sq = warp_sum(s_sq);
+    aux_sq = warp_sum(aux_sq);
+    if (lane == 0) {
+      sm.red[warp][S_SUMSQ] = s_sq;
+      sm.red[warp][S_AUXSQ] = aux_sq;
     }
   }
   __syncthreads();
-  if (stats && tid < kStatN) {
-    float v;
-    if (tid == S_SUM || tid == S_SUMSQ || (kTailMode == TAIL_SSI && tid == S_AUXSQ)) v = (sm.red[0][tid] + sm.red[1][tid]) + (sm.red[2][tid] + sm.red[3][tid]);
-    else if (tid == S_MIN || tid == S_MINU) v = fminf(fminf(sm.red[0][tid], sm.red[1][tid]), fminf(sm.red[2][tid], sm.red[3][tid]));
-    else if (tid == S_MAX || tid == S_MAXU) v = fmaxf(fmaxf(sm.red[0][tid], sm.red[1][tid]), fmaxf(sm.red[2][tid], sm.red[3][tid]));
-    else v = 0.f;
-    st_out[tid] = v;
+  if (kTailMode == TAIL_AFFINE) {
+    if (tid < kStatN) {
+      float v;
+      if (tid == S_SUM || tid == S_SUMSQ) v = (sm.red[0][tid] + sm.red[1][tid]) + (sm.red[2][tid] + sm.red[3][tid]);
+      else if (tid == S_MIN || tid == S_MINU) v = fminf(fminf(sm.red[0][tid], sm.red[1][tid]), fminf(sm.red[2][tid], sm.red[3][tid]));
+      else if (tid == S_MAX || tid == S_MAXU) v = fmaxf(fmaxf(sm.red[0][tid], sm.red[1][tid]), fmaxf(sm.red[2][tid], sm.red[3][tid]));
+      else v = 0.f;
+      st_out[tid] = v;
+    }
+  } else if (kTailMode == TAIL_SSI) {
+    if (tid == S_SUMSQ || tid == S_AUXSQ) st_out[tid] = (sm.red[0][tid] + sm.red[1][tid]) + (sm.red[2][tid] + sm.red[3][tid]);
   }
   float* yrow = y + (size_t)u * ld + tile0;
   const int valid = min(kTile, len - tile0);
@@ -612,13 +665,15 @@ int launch_fir_bank(const float* x, const int32_t* len, int B, int ld, const flo
   }
   // gridDim.y is limited to 65535: split very large batches over several launches.
   // tiles of the instantiation launched; the statistics (tails only) are laid out [B][tiles_for(ld)][kStatN]
-  const int ntiles = tail.mode == TAIL_NONE ? (ld + Geo<RB_KR_ONE>::kTile - 1) / Geo<RB_KR_ONE>::kTile : tiles_for(ld);
+  const int ntiles = tail.mode == TAIL_NONE  ? (ld + Geo<RB_KR_ONE>::kTile - 1) / Geo<RB_KR_ONE>::kTile
+                     : tail.mode == TAIL_SSI ? (ld + Geo<RB_KR_SSI>::kTile - 1) / Geo<RB_KR_SSI>::kTile
+                                             : tiles_for(ld);
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = min(65535, B - b0);
     dim3 grid(ntiles, nb);
     profile_begin(st);
     auto kernel = tail.mode == TAIL_AFFINE ? fir_bank_kernel<TAIL_AFFINE, kR>
-                  : tail.mode == TAIL_SSI  ? fir_bank_kernel<TAIL_SSI, kR>
+                  : tail.mode == TAIL_SSI  ? fir_bank_kernel<TAIL_SSI, RB_KR_SSI>
                                            : fir_bank_kernel<TAIL_NONE, RB_KR_ONE>;
     // Largest shared-memory carve-out: the kernel itself needs little L1, and the device planner's kernels (up to ~100 KB of
     // shared memory per CTA) can then run in what the four FIR CTAs of an SM leave free instead of waiting for them.
