@@ -67,9 +67,12 @@ def test_filter_fir_golden(eng, golden, K):
     assert max_err(y, ref) <= TOL * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("K,L", [(513, 3000), (700, 9000), (1500, 5200), (2049, 2600), (491, 1), (7, 2561), (24, 2560)])
+@pytest.mark.parametrize("K,L", [(513, 3000), (700, 9000), (1500, 5200), (2049, 2600), (491, 1), (7, 2561), (24, 2560),
+                                 (7, 3584), (24, 3585), (131, 7167), (131, 7168), (491, 7169), (51, 10752), (271, 11008), (1001, 14337)])
 def test_filter_fir_long_and_edge(eng, K, L):
-    """Filters longer than one staged segment (512 taps) and tile-boundary lengths."""
+    """Filters longer than one staged segment (512 taps) and tile-boundary lengths -- of the 2560-output tile of the bank and
+    of the 3584-output tile the plain filter runs with, including rows whose middle tiles take the batched staging path while
+    the first and last ones take the zero-filling one."""
     rs = np.random.RandomState(K * 7 + L)
     x = rs.standard_normal(L).astype(np.float32)
     b = rs.standard_normal(K) / np.sqrt(K)
