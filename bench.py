@@ -227,7 +227,7 @@ def build_id() -> str:
     h = hashlib.sha1()
     base = os.path.join(ROOT, "scl-deepfake-audio-detection_b200", "csrc")
     for name in sorted(os.listdir(base)):
-        if name.endswith((".cu", ".cuh", ".cpp")):
+        if name.endswith((".cu", ".cuh", ".cpp", ".sh")):  # build.sh carries the compile flags
             with open(os.path.join(base, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
     with open(os.path.join(ROOT, "include", "rawboost_b200.h"), "rb") as f:
@@ -405,7 +405,9 @@ class Bench:
             rec["roofline"] = {
                 "bound": "fp32", "kernel": "fir_bank_kernel", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                 "traffic": traffic_for("fir_bank_kernel", algo, B),
-                "peak_source": "FFMA2 register-resident chain measured in this run (rb_probe_fp32); scalar FFMA chain gave %.1f; "
+                "peak_source": "FFMA2 register-resident chain measured in this run (rb_probe_fp32; multiplier in a uniform register, "
+                               "two register-file operands per FFMA2: 99 %% of SMs x 128 lanes x 2 x clock -- the round-1 probe with "
+                               "three register operands measured 2 %% less); scalar FFMA chain gave %.1f; "
                                "MEASURED_PEAKS.json carries HBM and bf16-tensor peaks only and north_star puts this path on the "
                                "non-tensor FP32 pipe" % ffma,
                 "kernel_ms_per_launch": fir_avg_ms, "kernel_launches_per_step": per_step,

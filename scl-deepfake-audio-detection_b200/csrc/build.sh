@@ -12,7 +12,11 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
        -Xptxas -v -I"$root/include" -I"$here" ${RB_EXTRA_FLAGS:-})
 objs=()
 for src in rb_fir_bank rb_dense rb_api rb_probe rb_devplan rb_multiview; do
-  "$NVCC" "${FLAGS[@]}" -c "$here/$src.cu" -o "$out/$name.$src.o" 2> "$out/$name.$src.ptxas.log" || { cat "$out/$name.$src.ptxas.log" >&2; exit 1; }
+  extra=()
+  # the FP32 peak probe wants its multiplier in a uniform register (FFMA2 R, R, UR, R: two register-file operands instead of
+  # three); ptxas does that at the lower register-usage levels only (rb_probe.cu)
+  [ "$src" = rb_probe ] && extra=(-Xptxas --register-usage-level=3)
+  "$NVCC" "${FLAGS[@]}" "${extra[@]}" -c "$here/$src.cu" -o "$out/$name.$src.o" 2> "$out/$name.$src.ptxas.log" || { cat "$out/$name.$src.ptxas.log" >&2; exit 1; }
   objs+=("$out/$name.$src.o")
 done
 # host-only planner: plain g++ (function multiversioning for the MT19937 block)

@@ -11,6 +11,12 @@ constexpr int kProbeThreads = 256;
 constexpr int kProbeAcc = 16;      // independent accumulator pairs per thread
 constexpr int kProbeInner = 64;    // unrolled FMAs per accumulator per outer iteration
 
+// The multiplier `a` is uniform across the grid; built with -Xptxas --register-usage-level=3 (csrc/build.sh) ptxas keeps it in
+// a uniform register (`FFMA2 R, R, UR, R`), so each FFMA2 reads two register pairs instead of three and issues every 2 cycles
+// without depending on the operand-reuse cache: 73.9 TFLOP/s = 99 % of 148 SMs x 128 lanes x 2 x 1.965 GHz. At the default
+// level the multiplier sits in a vector register, every sixth FFMA2 goes without a reuse flag, and the same chain measures
+// 72.3 (profiles/r02m_register_usage_level.log). The higher figure is the pipe's attainable rate, hence the roofline
+// denominator; tests/test_host_logic.py checks that the built probe has the uniform-register form.
 template <bool PACKED>
 __global__ void __launch_bounds__(kProbeThreads)
 fp32_probe_kernel(int iters, float seed, float* __restrict__ sink) {

@@ -83,6 +83,29 @@ def test_filter_fir_long_and_edge(eng, K, L):
     assert max_err(orc.filter_fir(x, b), ref) <= 1e-6  # the closed form is the reference formula
 
 
+def test_filter_fir_ragged_batch(eng):
+    """One rb_filter_fir launch over rows of different lengths and tap counts: every row equals the closed form of filterFIR on
+    its own samples, whatever lies in the row's padding beyond its length (the batched staging path reads whole float4 chunks
+    only inside [0, len); the edge tiles zero-fill), and nothing is written beyond a row's length."""
+    lens = [1, 5, 2559, 3583, 3584, 3585, 7168, 9001, 12000, 14336, 14337, 20000]
+    Ks = [3, 51, 131, 7, 491, 24, 271, 700, 11, 1, 99, 513]
+    ld = 20000
+    rs = np.random.RandomState(99)
+    x = rs.standard_normal((len(lens), ld)).astype(np.float32) * 100.0  # the padding is loud garbage
+    taps = [(rs.standard_normal(K) / np.sqrt(K)).astype(np.float32) for K in Ks]
+    off = np.concatenate([[0], np.cumsum(Ks)]).astype(np.int32)
+    rows = [rs.uniform(-1, 1, L).astype(np.float32) for L in lens]
+    for r, (L, row) in enumerate(zip(lens, rows)):
+        x[r, :L] = row
+    out = torch.full((len(lens), ld), 7.0, dtype=torch.float32, device="cuda")
+    y = eng.filter_fir(torch.from_numpy(x).cuda(), torch.tensor(lens, dtype=torch.int32, device="cuda"),
+                       torch.from_numpy(np.concatenate(taps)).cuda(), torch.from_numpy(off).cuda(), out=out).cpu().numpy()
+    for r, (L, row, t) in enumerate(zip(lens, rows, taps)):
+        ref = orc.filter_fir_closed_form(row, t)
+        assert max_err(y[r, :L], ref) <= TOL * max(1.0, np.abs(ref).max()), f"row {r} (L={L}, K={t.shape[0]})"
+        assert np.all(y[r, L:] == 7.0), f"row {r}: samples beyond the row's length were written"
+
+
 def test_filter_fir_linearity_full_size(eng):
     """Size-independent property at BASELINE size: FIR(a*x1 + x2) == a*FIR(x1) + FIR(x2) (to fp32 rounding)."""
     B, L = 64, 64600

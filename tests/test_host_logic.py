@@ -385,6 +385,24 @@ def test_fir_kernel_sass_contract():
         assert regs and max(regs) <= 128, f"more than 128 registers: fewer than 4 CTAs of 128 threads per SM ({regs})"
 
 
+def test_fp32_peak_probe_uses_the_uniform_register_form():
+    """The roofline denominator of the FIR kernels is measured by rb_probe_fp32; its FFMA2 chain must be the fast form
+    (multiplier in a uniform register), or the peak -- and with it every reported fraction -- would be off by 2 %."""
+    import shutil
+    import subprocess
+    from scl_deepfake_audio_detection_b200 import _lib
+    if shutil.which("cuobjdump") is None or not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "fp32_probe_kernel", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if "FFMA2" not in sass:  # older cuobjdump: no -fun filter on mangled substrings
+        sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+        sass = sass[sass.index("fp32_probe_kernelILb1"):]
+        sass = sass[:sass.index("Function :", 10)] if "Function :" in sass[10:] else sass
+    ffma2 = [l for l in sass.splitlines() if "FFMA2" in l]
+    assert len(ffma2) >= 1024
+    assert sum(" UR" in l for l in ffma2) >= 0.95 * len(ffma2), "the packed probe lost its uniform-register operand"
+
+
 def test_native_planner_self_check_and_state_layout_guard():
     """The default planner of the drop-in verifies itself against numpy before its first use and leaves the global stream alone;
     the raw-state exchange is only used when numpy's private layout is what it assumes."""
