@@ -227,7 +227,7 @@ def build_id() -> str:
     h = hashlib.sha1()
     base = os.path.join(ROOT, "scl-deepfake-audio-detection_b200", "csrc")
     for name in sorted(os.listdir(base)):
-        if name.endswith((".cu", ".cuh", ".cpp", ".sh")):  # build.sh carries the compile flags
+        if name.endswith((".cu", ".cuh", ".cpp", ".sh", ".py")):  # build.sh carries the compile flags, sass_reuse_patch.py the post-link step
             with open(os.path.join(base, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
     with open(os.path.join(ROOT, "include", "rawboost_b200.h"), "rb") as f:

@@ -24,5 +24,14 @@ CUDA_INC="$(dirname "$(dirname "$NVCC")")/include"
 "${CXX:-g++}" -O3 -std=c++17 -fPIC -fvisibility=hidden -I"$root/include" -I"$CUDA_INC" -c "$here/rb_planner.cpp" -o "$out/$name.rb_planner.o"
 objs+=("$out/$name.rb_planner.o")
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$out/$name.so" "${objs[@]}" -Xcompiler -fPIC
+# Post-link: operand-reuse flags / yield hints of the FFMA2 streams of fir_bank_kernel (control bits only, see sass_reuse_patch.py).
+# A failure leaves the unpatched library in place (same results, ~3-5 % slower FIR kernels) and says so.
+if [ -z "${RB_NO_SASS_PATCH:-}" ]; then
+  if CUOBJDUMP="$(dirname "$NVCC")/cuobjdump" python3 "$here/sass_reuse_patch.py" "$out/$name.so" "$out/$name.so.patched"; then
+    mv "$out/$name.so.patched" "$out/$name.so"
+  else
+    rm -f "$out/$name.so.patched"; echo "WARNING: sass_reuse_patch.py failed; $name.so is left as ptxas scheduled it" >&2
+  fi
+fi
 grep -h -E "Used [0-9]+ registers|spill" "$out"/$name.*.ptxas.log | sort | uniq -c | sort -rn | head -20
 echo "built $out/$name.so"
